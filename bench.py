@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: multi-scale deformable attention, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Metric (BASELINE.json): MSDA fwd+bwd algorithmic GB/s, reported against the measured HBM peak.
+Workload at every N: BASELINE.json configs[1], the DETRPose-S decoder shape at 640x640
+(8 heads x 32 channels, levels 80^2/40^2/20^2, 4 points, Len_q 1080), batch 64 per GPU,
+bf16 value / output / grad_out, fp32 locations / attention / gradient accumulation.
+A step = one pass of the path over the batch: forward launch, zero-fill of the fp32
+grad_value pyramid, backward launch.  Weak scaling: every rank owns its own 64 images, no
+data-path collective.
+
+Prints ONE JSON line (rank 0).  `value` = algorithmic bytes of all ranks / max-over-ranks device
+time with inputs resident in HBM; `e2e` = the same through the public autograd API with
+pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = the dominant (backward)
+kernel against MEASURED_PEAKS.json; `cpu_baseline` = the reference's CPU op sequence
+(oracle/msda_torch.py) on a bounded sample, timed on this box's host cores.
+
+`--impl reference` times that CPU op sequence alone (all host threads), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "msda_fwd_bwd_algorithmic_GBps"
+UNIT = "GB/s"
+WORKLOAD = "detrpose_s"
+BATCH_PER_GPU = 64
+CPU_SAMPLE_IMAGES = 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"], help="value/out/grad_out storage type")
+    ap.add_argument("--lq", type=int, default=None)
+    ap.add_argument("--degenerate", action="store_true", help="all P points coincide, uniform attention")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fwd-variant", type=int, default=-1)
+    ap.add_argument("--bwd-variant", type=int, default=-1)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the last committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_dims(args):
+    from detrpose_b200 import synthetic
+    w = dict(synthetic.WORKLOADS[args.workload])
+    if args.lq:
+        w["Lq"] = args.lq
+    return w
+
+
+def per_image_bytes(w, dtype):
+    from detrpose_b200 import synthetic
+    e = 2 if dtype == "bf16" else 4
+    return synthetic.algorithmic_bytes(1, w["Lq"], w["H"], w["Dh"], w["shapes"], w["P"], e_v=e, e_o=e, e_l=4, e_g=4)
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the reference's op sequence on host cores
+# --------------------------------------------------------------------------------------
+def time_cpu_reference(w, dtype, images, steps, warmup):
+    """Times oracle/msda_torch.core_fwd_bwd (the reference's CPU PyTorch path: L x F.grid_sample +
+    cat/mul/sum and its autograd backward) on `images` images of the workload, fp32 on CPU.
+    Bytes are counted with the configured workload's accounting so that both arms compare
+    the same work per image."""
+    from detrpose_b200 import synthetic
+    from oracle import msda_torch as otorch          # checker / CPU baseline only
+    inp = synthetic.make_inputs(images, w["Lq"], w["H"], w["Dh"], w["shapes"], w["P"], seed=0, device="cpu")
+    value = otorch.make_value_list(inp["memory"], w["H"], w["shapes"])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        otorch.core_fwd_bwd(value, w["shapes"], inp["locations"], inp["attention"], inp["grad_out"])
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    b_f, b_b = per_image_bytes(w, dtype)
+    total = sum(times)
+    gbps = images * (b_f + b_b) * len(times) / total / 1e9
+    return gbps, total / len(times) * 1e3, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload_dims(args)
+    gbps, ms, threads = time_cpu_reference(w, args.dtype, CPU_SAMPLE_IMAGES, args.steps, args.warmup)
+    sample = (f"{CPU_SAMPLE_IMAGES} images of {args.workload} per step, fwd+bwd, fp32 on CPU "
+              f"(reference op sequence: per-level F.grid_sample + cat/mul/sum, autograd backward); "
+              f"bytes counted with the {args.dtype} accounting of the GPU arm")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbps, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, w, images=CPU_SAMPLE_IMAGES),
+        "cpu_baseline": {"value": round(gbps, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(gbps, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, w, images):
+    return {"workload": f"DETRPose-S decoder MSDA core, 640x640, batch {images}/GPU, fwd+bwd, one decoder layer"
+                        if args.workload == "detrpose_s" else args.workload,
+            "images_per_gpu": images, "Lq": w["Lq"], "heads": w["H"], "head_dim": w["Dh"],
+            "levels": [list(s) for s in w["shapes"]], "points": w["P"],
+            "value_dtype": args.dtype, "loc_attn_dtype": "fp32", "grad_value_dtype": "fp32",
+            "value_layout": "channel-last (N,S,H,Dh) = reference `memory` (N,S,C), zero-copy",
+            "locations": "degenerate (P coincident, uniform attention)" if args.degenerate
+                         else "ref~U(0,1) + N(0,2px) offsets, clipped to [-0.1,1.1]",
+            "l2_policy": "inputs larger than L2 (value+loc+attn+grads per step >> 126 MB)"}
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch.distributed as dist
+    from detrpose_b200 import synthetic, shard, _lib
+    from detrpose_b200 import functional as MF
+    import detrpose_b200 as dp
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    lib.msda_b200_set_variant(args.fwd_variant, args.bwd_variant)
+
+    w = workload_dims(args)
+    vdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    N = args.batch
+    inp = synthetic.make_inputs(N, w["Lq"], w["H"], w["Dh"], w["shapes"], w["P"], seed=rank, device=dev,
+                                value_dtype=vdt, degenerate=args.degenerate)
+    shapes = inp["shapes"]
+    pyramid = MF.pack_value(inp["memory"], shapes, w["H"])            # zero-copy view
+    loc, att, go = inp["locations"], inp["attention"], inp["grad_out"]
+    grad_value = torch.empty((N, inp["S"], w["H"], w["Dh"]), dtype=torch.float32, device=dev)
+    grad_loc, grad_att = torch.empty_like(loc), torch.empty_like(att)
+    out = torch.empty((N, w["Lq"], w["H"] * w["Dh"]), dtype=vdt, device=dev)
+    code = MF._code
+    strides = _lib.i64_array(pyramid.stride()[:3])
+    shp = _lib.i32_array([d for hw in shapes for d in hw])
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+    cm = MF.get_default_coord_mode()
+    dims = (N, w["Lq"], w["H"], w["Dh"], len(shapes), w["P"])
+
+    def fwd():
+        _lib.check(lib.msda_b200_forward(pyramid.data_ptr(), code(vdt), strides, shp, loc.data_ptr(), att.data_ptr(),
+                                         out.data_ptr(), code(vdt), *dims, cm, sp), "forward")
+
+    def bwd():
+        _lib.check(lib.msda_b200_backward(pyramid.data_ptr(), code(vdt), strides, shp, loc.data_ptr(),
+                                          att.data_ptr(), go.data_ptr(), code(vdt), grad_value.data_ptr(),
+                                          grad_loc.data_ptr(), grad_att.data_ptr(), *dims, cm, sp), "backward")
+
+    def step(events=None):
+        if events is not None:
+            events[0].record(stream)
+        fwd()
+        if events is not None:
+            events[1].record(stream)
+        grad_value.zero_()
+        if events is not None:
+            events[2].record(stream)
+        bwd()
+        if events is not None:
+            events[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    per_step_events = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for i in range(args.steps):
+        step(per_step_events[i])
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    elapsed_ms = shard.max_over_ranks(elapsed_ms, device=dev)
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in per_step_events)
+    zero_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in per_step_events)
+    bwd_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in per_step_events)
+
+    b_f, b_b = per_image_bytes(w, args.dtype)
+    local_bytes = N * (b_f + b_b) * args.steps
+    total_bytes = shard.job_total(local_bytes, device=dev)
+    value = total_bytes / (elapsed_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- e2e: public autograd API, pinned host buffers, H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        host = {k: inp[k].cpu().pin_memory() for k in ("memory", "locations", "attention", "grad_out")}
+        d_mem = torch.empty_like(inp["memory"])
+        d_loc, d_att, d_go = torch.empty_like(loc), torch.empty_like(att), torch.empty_like(go)
+        h_out = torch.empty(out.shape, dtype=vdt).pin_memory()
+        h_gm = torch.empty(inp["memory"].shape, dtype=vdt).pin_memory()
+        h_gl, h_ga = torch.empty(loc.shape).pin_memory(), torch.empty(att.shape).pin_memory()
+        h2d = sum(host[k].numel() * host[k].element_size() for k in host)
+        d2h = sum(t.numel() * t.element_size() for t in (h_out, h_gm, h_gl, h_ga))
+
+        def e2e_step():
+            d_mem.copy_(host["memory"], non_blocking=True)
+            d_loc.copy_(host["locations"], non_blocking=True)
+            d_att.copy_(host["attention"], non_blocking=True)
+            d_go.copy_(host["grad_out"], non_blocking=True)
+            m = d_mem.requires_grad_(True)
+            l = d_loc.requires_grad_(True)
+            a = d_att.requires_grad_(True)
+            o = dp.ms_deform_attn_core(m, shapes, l, a)
+            gm, gl, ga = torch.autograd.grad(o, [m, l, a], d_go)
+            h_out.copy_(o.detach(), non_blocking=True)
+            h_gm.copy_(gm, non_blocking=True)
+            h_gl.copy_(gl, non_blocking=True)
+            h_ga.copy_(ga, non_blocking=True)
+            d_mem.requires_grad_(False), d_loc.requires_grad_(False), d_att.requires_grad_(False)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        e2e_ms = shard.max_over_ranks(e0.elapsed_time(e1), device=dev)
+        e2e_bytes = shard.job_total(N * (b_f + b_b) * e2e_steps, device=dev)
+        e2e = {"value": round(e2e_bytes / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "ms_per_step": round(e2e_ms / e2e_steps, 3),
+               "api": "detrpose_b200.ms_deform_attn_core + torch.autograd.grad, pinned host buffers"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's CPU op sequence on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        gbps, ms, threads = time_cpu_reference(w, args.dtype, CPU_SAMPLE_IMAGES, steps=12, warmup=2)
+        cpu = {"value": round(gbps, 4), "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload x 12 timed fwd+bwd passes "
+                         f"({ms:.0f} ms each), fp32 on CPU via oracle/msda_torch.py (the reference's op sequence); "
+                         f"bytes counted with the {args.dtype} accounting of the GPU arm"}
+
+    if rank == 0:
+        traffic = ncu_traffic()
+        bwd_bytes = N * b_b
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed_ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": config_dict(args, w, images=N),
+            "frac_of_hbm_peak": round(value / world / peak, 4),
+            "kernels": {"forward_ms": round(fwd_ms, 4), "grad_zero_fill_ms": round(zero_ms, 4),
+                        "backward_ms": round(bwd_ms, 4),
+                        "forward_GBps": round(N * b_f / (fwd_ms * 1e-3) / 1e9, 1),
+                        "backward_GBps": round(N * b_b / (bwd_ms * 1e-3) / 1e9, 1)},
+            "roofline": {"kernel": "msda backward (grad_value + grad_locations + grad_attention)",
+                         "bound": "hbm", "achieved": round(bwd_bytes / (bwd_ms * 1e-3) / 1e9, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak, 4),
+                         "peak_source": peak_src,
+                         "traffic": traffic.get("backward_dram_bytes_per_launch") if traffic else None,
+                         "algorithmic_bytes_per_launch": int(bwd_bytes)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

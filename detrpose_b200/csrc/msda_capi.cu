@@ -1,0 +1,216 @@
+// C ABI (include/msda_b200.h): argument checking, problem description, kernel
+// selection.  No torch types, no global mutable state besides the per-thread
+// error string and the (atomic) kernel-variant knobs.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+std::atomic<int> g_fwd_variant{-1};   // -1: automatic
+std::atomic<int> g_bwd_variant{-1};
+
+// Validates sizes and fills the kernel-side problem description.
+int make_problem(msda::Problem& pb, int N, int Lq, int H, int Dh, int L, int P,
+                 const int32_t* spatial_shapes, int coord_mode) {
+    if (spatial_shapes == nullptr) return fail(MSDA_ERR_NULL, "spatial_shapes is NULL");
+    if (N <= 0 || Lq <= 0 || H <= 0 || L <= 0 || P <= 0)
+        return fail(MSDA_ERR_SHAPE, "non-positive size N=%d Lq=%d H=%d L=%d P=%d", N, Lq, H, L, P);
+    if (L > MSDA_MAX_LEVELS || P > MSDA_MAX_POINTS)
+        return fail(MSDA_ERR_LEVELS, "L=%d (max %d) or P=%d (max %d) too large", L, MSDA_MAX_LEVELS, P,
+                    MSDA_MAX_POINTS);
+    if (Dh < 8 || Dh > 128 || Dh % 8 != 0)
+        return fail(MSDA_ERR_DHEAD, "Dh=%d unsupported (multiple of 8 in 8..128)", Dh);
+    if (coord_mode != MSDA_COORD_UNFUSED && coord_mode != MSDA_COORD_FMA)
+        return fail(MSDA_ERR_SHAPE, "unknown coord_mode %d", coord_mode);
+    pb.N = N; pb.Lq = Lq; pb.H = H; pb.Dh = Dh; pb.L = L; pb.P = P;
+    pb.coord_mode = coord_mode;
+    int64_t acc = 0;
+    for (int l = 0; l < MSDA_MAX_LEVELS; ++l) {
+        if (l < L) {
+            const int32_t h = spatial_shapes[2 * l], w = spatial_shapes[2 * l + 1];
+            if (h <= 0 || w <= 0 || h > 16384 || w > 16384)
+                return fail(MSDA_ERR_SHAPE, "level %d has shape %dx%d", l, h, w);
+            pb.geom.h[l] = h; pb.geom.w[l] = w; pb.geom.start[l] = (int32_t)acc;
+            acc += (int64_t)h * w;
+            if (acc > (1 << 30)) return fail(MSDA_ERR_SHAPE, "pyramid too large");
+        } else {
+            pb.geom.h[l] = 1; pb.geom.w[l] = 1; pb.geom.start[l] = (int32_t)acc;
+        }
+    }
+    pb.S = (int32_t)acc;
+    pb.vs_n = (int64_t)pb.S * H * Dh; pb.vs_s = (int64_t)H * Dh; pb.vs_h = Dh;
+    return MSDA_OK;
+}
+
+int set_value_strides(msda::Problem& pb, const void* value, int value_dtype, const int64_t* strides) {
+    if (value == nullptr || strides == nullptr) return fail(MSDA_ERR_NULL, "value / value_strides is NULL");
+    if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16)
+        return fail(MSDA_ERR_DTYPE, "unknown value dtype %d", value_dtype);
+    const int es = value_dtype == MSDA_BF16 ? 2 : 4;
+    pb.vs_n = strides[0]; pb.vs_s = strides[1]; pb.vs_h = strides[2];
+    if (!aligned16(value) || (pb.vs_n * es) % 16 || (pb.vs_s * es) % 16 || (pb.vs_h * es) % 16)
+        return fail(MSDA_ERR_ALIGN, "value rows must be 16-byte aligned (ptr %p, strides %lld %lld %lld, %d B elems)",
+                    value, (long long)pb.vs_n, (long long)pb.vs_s, (long long)pb.vs_h, es);
+    if (pb.vs_s < 0 || pb.vs_h < 0 || pb.vs_n < 0) return fail(MSDA_ERR_SHAPE, "negative value stride");
+    return MSDA_OK;
+}
+
+int fill_views(msda::LevelViews& v, const void* const* ptrs, const int64_t* strides, int L) {
+    if (ptrs == nullptr || strides == nullptr) return fail(MSDA_ERR_NULL, "level_ptrs / level_strides is NULL");
+    for (int l = 0; l < MSDA_MAX_LEVELS; ++l) {
+        if (l < L) {
+            if (ptrs[l] == nullptr) return fail(MSDA_ERR_NULL, "level_ptrs[%d] is NULL", l);
+            v.ptr[l] = ptrs[l];
+            v.s_nh[l] = strides[3 * l]; v.s_c[l] = strides[3 * l + 1]; v.s_s[l] = strides[3 * l + 2];
+        } else {
+            v.ptr[l] = nullptr; v.s_nh[l] = v.s_c[l] = v.s_s[l] = 0;
+        }
+    }
+    return MSDA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+MSDA_API int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+MSDA_API const char* msda_b200_last_error(void) { return g_err; }
+
+MSDA_API int msda_b200_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(MSDA_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e)); }
+    int v = 0;
+    if (sm_count) { cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); *sm_count = v; }
+    if (cc_major) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev); *cc_major = v; }
+    if (cc_minor) { cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev); *cc_minor = v; }
+    return MSDA_OK;
+}
+
+MSDA_API int msda_b200_set_variant(int fwd_variant, int bwd_variant) {
+    g_fwd_variant.store(fwd_variant);
+    g_bwd_variant.store(bwd_variant);
+    return MSDA_OK;
+}
+
+MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t* value_strides,
+                      const int32_t* spatial_shapes, const float* locations, const float* attention,
+                      void* out, int out_dtype, int N, int Lq, int H, int Dh, int L, int P,
+                      int coord_mode, void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, coord_mode);
+    if (rc) return rc;
+    if ((rc = set_value_strides(pb, value, value_dtype, value_strides))) return rc;
+    if (!locations || !attention || !out) return fail(MSDA_ERR_NULL, "locations / attention / out is NULL");
+    if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16) return fail(MSDA_ERR_DTYPE, "unknown out dtype %d", out_dtype);
+    if (!aligned16(out) || !aligned16(locations) || !aligned16(attention))
+        return fail(MSDA_ERR_ALIGN, "locations / attention / out must be 16-byte aligned");
+    const cudaError_t e = msda::forward_flat(pb, value, value_dtype == MSDA_BF16, locations, attention, out,
+                                             out_dtype == MSDA_BF16, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward launch");
+}
+
+MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_t* value_strides,
+                       const int32_t* spatial_shapes, const float* locations, const float* attention,
+                       const void* grad_out, int grad_out_dtype, float* grad_value, float* grad_locations,
+                       float* grad_attention, int N, int Lq, int H, int Dh, int L, int P, int coord_mode,
+                       void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, coord_mode);
+    if (rc) return rc;
+    if ((rc = set_value_strides(pb, value, value_dtype, value_strides))) return rc;
+    if (!locations || !attention || !grad_out) return fail(MSDA_ERR_NULL, "locations / attention / grad_out is NULL");
+    if ((grad_locations == nullptr) != (grad_attention == nullptr))
+        return fail(MSDA_ERR_NULL, "grad_locations and grad_attention must be given together");
+    if (grad_out_dtype != MSDA_F32 && grad_out_dtype != MSDA_BF16)
+        return fail(MSDA_ERR_DTYPE, "unknown grad_out dtype %d", grad_out_dtype);
+    if (!aligned16(grad_out) || !aligned16(locations) || !aligned16(attention) ||
+        (grad_value && !aligned16(grad_value)) || (grad_locations && !aligned16(grad_locations)))
+        return fail(MSDA_ERR_ALIGN, "backward buffers must be 16-byte aligned");
+    if (!grad_value && !grad_locations) return MSDA_OK;
+    const cudaError_t e = msda::backward_flat(pb, value, value_dtype == MSDA_BF16, locations, attention, grad_out,
+                                              grad_out_dtype == MSDA_BF16, grad_value, grad_locations,
+                                              grad_attention, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_backward launch");
+}
+
+MSDA_API int msda_b200_sample_indices(const int32_t* spatial_shapes, const float* locations, int32_t* idx_out,
+                             int32_t* level_start_out, int N, int Lq, int H, int L, int P, int coord_mode,
+                             void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, 8, L, P, spatial_shapes, coord_mode);
+    if (rc) return rc;
+    if (!locations || !idx_out) return fail(MSDA_ERR_NULL, "locations / idx_out is NULL");
+    const cudaError_t e = msda::sample_indices(pb, locations, idx_out, level_start_out, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_sample_indices launch");
+}
+
+MSDA_API int msda_b200_locations(const float* offsets, const float* logits, const float* ref_points, int ref_levels,
+                        const int32_t* spatial_shapes, float* locations, float* attention, int N, int Lq,
+                        int H, int L, int P, void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, 8, L, P, spatial_shapes, MSDA_COORD_UNFUSED);
+    if (rc) return rc;
+    if (!offsets || !logits || !ref_points || !locations || !attention)
+        return fail(MSDA_ERR_NULL, "a prologue buffer is NULL");
+    if (ref_levels != 1 && ref_levels != L)
+        return fail(MSDA_ERR_SHAPE, "ref_levels=%d must be 1 or L=%d", ref_levels, L);
+    const cudaError_t e = msda::locations(pb, offsets, logits, ref_points, ref_levels, locations, attention,
+                                          (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_locations launch");
+}
+
+MSDA_API int msda_b200_repack(const void* const* level_ptrs, const int64_t* level_strides, int src_dtype,
+                     const int32_t* spatial_shapes, void* dst, int dst_dtype, int N, int H, int Dh, int L,
+                     void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, 1, H, Dh, L, 1, spatial_shapes, MSDA_COORD_UNFUSED);
+    if (rc) return rc;
+    msda::LevelViews v;
+    if ((rc = fill_views(v, level_ptrs, level_strides, L))) return rc;
+    if (!dst) return fail(MSDA_ERR_NULL, "dst is NULL");
+    if ((src_dtype != MSDA_F32 && src_dtype != MSDA_BF16) || (dst_dtype != MSDA_F32 && dst_dtype != MSDA_BF16))
+        return fail(MSDA_ERR_DTYPE, "unknown dtype %d / %d", src_dtype, dst_dtype);
+    if ((int64_t)N * H > 65535) return fail(MSDA_ERR_SHAPE, "N*H=%lld exceeds 65535", (long long)N * H);
+    const cudaError_t e = msda::repack(pb, v, src_dtype == MSDA_BF16, dst, dst_dtype == MSDA_BF16, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_repack launch");
+}
+
+MSDA_API int msda_b200_unpack_grad(const float* grad_value, const int32_t* spatial_shapes, void* const* level_ptrs,
+                          const int64_t* level_strides, int dst_dtype, int N, int H, int Dh, int L,
+                          void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, 1, H, Dh, L, 1, spatial_shapes, MSDA_COORD_UNFUSED);
+    if (rc) return rc;
+    msda::LevelViews v;
+    if ((rc = fill_views(v, (const void* const*)level_ptrs, level_strides, L))) return rc;
+    if (!grad_value) return fail(MSDA_ERR_NULL, "grad_value is NULL");
+    if (dst_dtype != MSDA_F32 && dst_dtype != MSDA_BF16) return fail(MSDA_ERR_DTYPE, "unknown dtype %d", dst_dtype);
+    if ((int64_t)N * H > 65535) return fail(MSDA_ERR_SHAPE, "N*H=%lld exceeds 65535", (long long)N * H);
+    const cudaError_t e = msda::unpack_grad(pb, grad_value, v, dst_dtype == MSDA_BF16, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_unpack_grad launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,34 @@
+// Internal launcher declarations shared by the C-ABI translation unit.
+#pragma once
+
+#include "msda_common.cuh"
+
+namespace msda {
+
+constexpr int kFwdThreads = 256;
+constexpr int kBwdThreads = 256;
+
+// msda_fwd.cu
+cudaError_t forward_flat(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                         const float* attn, void* out, bool out_bf16, cudaStream_t st);
+
+// msda_bwd.cu
+cudaError_t backward_flat(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                          const float* attn, const void* grad_out, bool go_bf16, float* grad_value,
+                          float* grad_loc, float* grad_attn, cudaStream_t st);
+
+// msda_aux.cu
+cudaError_t sample_indices(const Problem& pb, const float* loc, int32_t* idx_out,
+                           int32_t* level_start_out, cudaStream_t st);
+cudaError_t locations(const Problem& pb, const float* offsets, const float* logits, const float* ref,
+                      int ref_levels, float* loc, float* attn, cudaStream_t st);
+struct LevelViews {
+    const void* ptr[MSDA_MAX_LEVELS];
+    int64_t s_nh[MSDA_MAX_LEVELS], s_c[MSDA_MAX_LEVELS], s_s[MSDA_MAX_LEVELS];
+};
+cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void* dst, bool dst_bf16,
+                   cudaStream_t st);
+cudaError_t unpack_grad(const Problem& pb, const float* grad_value, const LevelViews& dst, bool dst_bf16,
+                        cudaStream_t st);
+
+}  // namespace msda

@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference's sampling core over the C-ABI kernels.
+
+``ms_deform_attn_core`` has the argument meaning of the reference's
+``ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations,
+attention_weights)`` (/root/reference/src/models/detrpose/ms_deform_attn.py:145-193):
+``value`` is the list of per-level tensors ``(N*H, Dh, H_l*W_l)`` with
+arbitrary strides that ``Transformer.forward`` builds (transformer.py:1285-1286),
+the result is ``(N, Lq, H*Dh)``, and it is differentiable w.r.t. the value
+list, the locations and the attention weights.
+
+PyTorch is used here for device memory, streams and autograd plumbing only;
+all arithmetic runs in ``libmsda_b200.so``.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import List, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+
+__all__ = [
+    "ms_deform_attn_core", "sample_indices", "level_start_index", "locations_and_weights",
+    "pack_value", "clear_repack_cache", "set_default_coord_mode", "get_default_coord_mode",
+]
+
+_DTYPE_CODE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+# Rounding chain for the pixel coordinate (see include/msda_b200.h).  UNFUSED is the
+# reference's elementwise-op chain; tests/gpu decide which one ATen's CUDA sampler uses.
+_default_coord_mode = _lib.COORD_UNFUSED
+
+
+def set_default_coord_mode(mode: int) -> None:
+    global _default_coord_mode
+    if mode not in (_lib.COORD_UNFUSED, _lib.COORD_FMA):
+        raise ValueError(f"unknown coord mode {mode}")
+    _default_coord_mode = mode
+
+
+def get_default_coord_mode() -> int:
+    return _default_coord_mode
+
+
+def level_start_index(spatial_shapes: Sequence[Sequence[int]]) -> List[int]:
+    """Offsets of each level in the flattened pyramid (exclusive running sum of H_l*W_l)."""
+    starts, acc = [], 0
+    for h, w in spatial_shapes:
+        starts.append(acc)
+        acc += int(h) * int(w)
+    return starts
+
+
+def _shapes_tuple(spatial_shapes) -> Tuple[Tuple[int, int], ...]:
+    if isinstance(spatial_shapes, torch.Tensor):
+        spatial_shapes = spatial_shapes.tolist()
+    return tuple((int(h), int(w)) for h, w in spatial_shapes)
+
+
+def _code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPE_CODE[dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {dtype}: the kernels take float32 or bfloat16") from None
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: detrpose_b200 has no CPU path")
+
+
+# --------------------------------------------------------------------------
+# value layout: list of strided per-level views  ->  channel-last pyramid
+# --------------------------------------------------------------------------
+class _RepackCache:
+    """One-entry cache so that the decoder layers sharing one value list repack once.
+
+    Keyed on the identity of ``value[0]`` (held weakly) and the version counters of
+    every level, so a new forward pass -- new view objects, even at the same
+    address -- never hits a stale entry.
+    """
+
+    def __init__(self):
+        self._ref = None
+        self._sig = None
+        self._pyramid = None
+
+    def get(self, levels):
+        if self._ref is None or self._ref() is not levels[0]:
+            return None
+        if self._sig != self._signature(levels):
+            return None
+        return self._pyramid
+
+    def put(self, levels, pyramid):
+        self._ref = weakref.ref(levels[0])
+        self._sig = self._signature(levels)
+        self._pyramid = pyramid
+
+    def clear(self):
+        self._ref = self._sig = self._pyramid = None
+
+    @staticmethod
+    def _signature(levels):
+        return tuple((id(v), v._version, v.data_ptr(), tuple(v.shape), tuple(v.stride())) for v in levels)
+
+
+_repack_cache = _RepackCache()
+stats = {"repack_launches": 0, "forward_launches": 0, "backward_launches": 0}   # launch counters (tests, bench)
+
+
+def clear_repack_cache() -> None:
+    _repack_cache.clear()
+
+
+def _zero_copy_view(levels, shapes, n_heads):
+    """Return a (N, S, H, Dh) view if the level list already is one channel-last pyramid."""
+    v0 = levels[0]
+    nh, dh, _ = v0.shape
+    if v0.stride(1) != 1 or nh % n_heads:
+        return None
+    n = nh // n_heads
+    es = v0.element_size()
+    s_nh, s_s = v0.stride(0), v0.stride(2)
+    base = v0.untyped_storage().data_ptr()
+    acc = 0
+    for v, (h, w) in zip(levels, shapes):
+        if (v.stride(0), v.stride(1), v.stride(2)) != (s_nh, 1, s_s):
+            return None
+        if v.untyped_storage().data_ptr() != base or v.data_ptr() != v0.data_ptr() + acc * s_s * es:
+            return None
+        acc += h * w
+    if (s_nh * es) % 16 or (s_s * es) % 16 or v0.data_ptr() % 16:
+        return None
+    return torch.as_strided(v0, (n, acc, n_heads, dh), (n_heads * s_nh, s_s, s_nh, 1), v0.storage_offset())
+
+
+def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> torch.Tensor:
+    """Bring ``value`` into the kernel-native layout ``(N, S, H, Dh)`` (channel stride 1).
+
+    Accepts the reference's list of ``(N*H, Dh, H_l*W_l)`` views (zero-copy when
+    they already are channel-innermost views of one buffer -- the N == 1 case of
+    transformer.py:1285-1286 -- otherwise one repack kernel), or a single tensor
+    ``(N, S, C)`` / ``(N, S, H, Dh)`` such as the reference's ``memory``.
+    """
+    shapes = _shapes_tuple(spatial_shapes)
+    total = sum(h * w for h, w in shapes)
+    if isinstance(value, torch.Tensor):
+        _require_cuda(value, "value")
+        if value.dim() == 3:
+            value = value.unflatten(2, (n_heads, -1))
+        if value.dim() != 4 or value.shape[1] != total or value.shape[2] != n_heads:
+            raise ValueError(f"value tensor must be (N, S={total}, C) or (N, S, H={n_heads}, Dh), got {tuple(value.shape)}")
+        if value.stride(3) != 1 or any((s * value.element_size()) % 16 for s in value.stride()[:3]) \
+                or value.data_ptr() % 16:
+            value = value.contiguous()
+        return value
+    levels = list(value)
+    if len(levels) != len(shapes):
+        raise ValueError(f"{len(levels)} value levels but {len(shapes)} spatial shapes")
+    for v, (h, w) in zip(levels, shapes):
+        _require_cuda(v, "value")
+        if v.dim() != 3 or v.shape[2] != h * w or v.shape[:2] != levels[0].shape[:2]:
+            raise ValueError(f"value level of shape {tuple(v.shape)} does not match (N*H, Dh, {h}*{w})")
+    view = _zero_copy_view(levels, shapes, n_heads)
+    if view is not None:
+        return view
+    if use_cache:
+        hit = _repack_cache.get(levels)
+        if hit is not None:
+            return hit
+    nh, dh, _ = levels[0].shape
+    if nh % n_heads:
+        raise ValueError(f"value leading dim {nh} is not a multiple of n_heads={n_heads}")
+    n = nh // n_heads
+    dtype = levels[0].dtype
+    if dtype not in _DTYPE_CODE:                 # e.g. fp16 under the reference's AMP: sampler runs fp32
+        levels = [v.float() for v in levels]
+        dtype = torch.float32
+    pyramid = torch.empty((n, total, n_heads, dh), dtype=dtype, device=levels[0].device)
+    lib = _lib.load()
+    with torch.cuda.device(pyramid.device):
+        rc = lib.msda_b200_repack(
+            _lib.ptr_array([v.data_ptr() for v in levels]),
+            _lib.i64_array([s for v in levels for s in v.stride()]),
+            _code(dtype), _lib.i32_array([d for hw in shapes for d in hw]),
+            pyramid.data_ptr(), _code(dtype), n, n_heads, dh, len(shapes), _stream_ptr(pyramid.device))
+    _lib.check(rc, "msda_b200_repack")
+    stats["repack_launches"] += 1
+    if use_cache:
+        _repack_cache.put(list(value), pyramid)
+    return pyramid
+
+
+# --------------------------------------------------------------------------
+# raw launches (no autograd)
+# --------------------------------------------------------------------------
+def _forward_raw(pyramid, shapes, loc, attn, out_dtype, coord_mode):
+    n, _, n_heads, dh = pyramid.shape
+    _, lq, _, n_levels, n_points, _ = loc.shape
+    out = torch.empty((n, lq, n_heads * dh), dtype=out_dtype, device=pyramid.device)
+    lib = _lib.load()
+    with torch.cuda.device(pyramid.device):
+        rc = lib.msda_b200_forward(
+            pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
+            _lib.i32_array([d for hw in shapes for d in hw]),
+            loc.data_ptr(), attn.data_ptr(), out.data_ptr(), _code(out_dtype),
+            n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(pyramid.device))
+    _lib.check(rc, "msda_b200_forward")
+    stats["forward_launches"] += 1
+    return out
+
+
+def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, coord_mode):
+    n, total, n_heads, dh = pyramid.shape
+    _, lq, _, n_levels, n_points, _ = loc.shape
+    dev = pyramid.device
+    grad_value = torch.zeros((n, total, n_heads, dh), dtype=torch.float32, device=dev) if need_value else None
+    grad_loc = torch.empty_like(loc) if need_small else None
+    grad_attn = torch.empty_like(attn) if need_small else None
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        rc = lib.msda_b200_backward(
+            pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
+            _lib.i32_array([d for hw in shapes for d in hw]),
+            loc.data_ptr(), attn.data_ptr(), grad_out.data_ptr(), _code(grad_out.dtype),
+            grad_value.data_ptr() if need_value else None,
+            grad_loc.data_ptr() if need_small else None,
+            grad_attn.data_ptr() if need_small else None,
+            n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(dev))
+    _lib.check(rc, "msda_b200_backward")
+    stats["backward_launches"] += 1
+    return grad_value, grad_loc, grad_attn
+
+
+def _unpack_grad(grad_value, shapes, n_heads, dtype):
+    """fp32 channel-last grad pyramid -> list of (N*H, Dh, H_l*W_l) grads (views of one buffer)."""
+    n, total, _, dh = grad_value.shape
+    buf = torch.empty((n * n_heads, dh, total), dtype=dtype, device=grad_value.device)
+    levels = list(buf.split([h * w for h, w in shapes], dim=-1))
+    lib = _lib.load()
+    with torch.cuda.device(buf.device):
+        rc = lib.msda_b200_unpack_grad(
+            grad_value.data_ptr(), _lib.i32_array([d for hw in shapes for d in hw]),
+            _lib.ptr_array([v.data_ptr() for v in levels]),
+            _lib.i64_array([s for v in levels for s in v.stride()]),
+            _code(dtype), n, n_heads, dh, len(shapes), _stream_ptr(buf.device))
+    _lib.check(rc, "msda_b200_unpack_grad")
+    return levels
+
+
+def _as_f32_contig(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class _MSDACore(torch.autograd.Function):
+    """out = core(loc, attn, *value); value is one pyramid tensor or L per-level tensors."""
+
+    @staticmethod
+    def forward(ctx, loc, attn, meta, *value):
+        shapes, n_heads, coord_mode, out_dtype, is_list = meta
+        pyramid = pack_value(list(value) if is_list else value[0], shapes, n_heads)
+        loc_c, attn_c = _as_f32_contig(loc), _as_f32_contig(attn)
+        out = _forward_raw(pyramid, shapes, loc_c, attn_c, out_dtype or pyramid.dtype, coord_mode)
+        ctx.meta = meta
+        ctx.pyramid = pyramid
+        ctx.value_meta = [(tuple(v.shape), v.dtype) for v in value]
+        ctx.small_dtypes = (loc.dtype, attn.dtype)
+        ctx.save_for_backward(loc_c, attn_c)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        shapes, n_heads, coord_mode, _, is_list = ctx.meta
+        loc_c, attn_c = ctx.saved_tensors
+        need_small = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_value = any(ctx.needs_input_grad[3:])
+        if grad_out.dtype not in _DTYPE_CODE:
+            grad_out = grad_out.float()
+        grad_out = grad_out.contiguous()
+        gv, gl, ga = _backward_raw(ctx.pyramid, shapes, loc_c, attn_c, grad_out, need_value, need_small,
+                                   coord_mode)
+        value_grads = [None] * len(ctx.value_meta)
+        if need_value:
+            if is_list:
+                dtype = ctx.value_meta[0][1]
+                value_grads = _unpack_grad(gv, shapes, n_heads, dtype if dtype in _DTYPE_CODE else torch.float32)
+                value_grads = [g.to(m[1]) for g, m in zip(value_grads, ctx.value_meta)]
+            else:
+                shape, dtype = ctx.value_meta[0]
+                value_grads = [gv.reshape(shape).to(dtype)]
+        if gl is not None:
+            gl, ga = gl.to(ctx.small_dtypes[0]), ga.to(ctx.small_dtypes[1])
+        return (gl, ga, None, *value_grads)
+
+
+def ms_deform_attn_core(value, value_spatial_shapes, sampling_locations, attention_weights,
+                        *, n_heads: int = None, out_dtype: torch.dtype = None,
+                        coord_mode: int = None) -> torch.Tensor:
+    """Multi-scale deformable attention sampling core on B200 (forward + autograd).
+
+    Same argument meaning and result as the reference's
+    ``ms_deform_attn_core_pytorch`` (ms_deform_attn.py:145-193) with its optional
+    flags off.  ``value`` may also be one ``(N, S, C)`` / ``(N, S, H, Dh)`` tensor
+    (the reference's ``memory``), which is consumed zero-copy.
+    """
+    _require_cuda(sampling_locations, "sampling_locations")
+    if sampling_locations.dim() != 6 or sampling_locations.shape[-1] != 2:
+        raise ValueError("sampling_locations must be (N, Lq, H, L, P, 2)")
+    n, lq, heads, n_levels, n_points, _ = sampling_locations.shape
+    if tuple(attention_weights.shape) != (n, lq, heads, n_levels, n_points):
+        raise ValueError("attention_weights must be (N, Lq, H, L, P) matching sampling_locations")
+    if n_heads is not None and n_heads != heads:
+        raise ValueError(f"n_heads={n_heads} but sampling_locations has {heads} heads")
+    shapes = _shapes_tuple(value_spatial_shapes)
+    if len(shapes) != n_levels:
+        raise ValueError(f"{len(shapes)} spatial shapes for {n_levels} levels")
+    if n_levels > _lib.MAX_LEVELS or n_points > _lib.MAX_POINTS:
+        raise ValueError(f"at most {_lib.MAX_LEVELS} levels and {_lib.MAX_POINTS} points are supported")
+    is_list = not isinstance(value, torch.Tensor)
+    meta = (shapes, heads, _default_coord_mode if coord_mode is None else coord_mode, out_dtype, is_list)
+    args = tuple(value) if is_list else (value,)
+    return _MSDACore.apply(sampling_locations, attention_weights, meta, *args)
+
+
+def sample_indices(sampling_locations: torch.Tensor, spatial_shapes, coord_mode: int = None):
+    """Integer corner indices ``(y0, x0)`` per sample and the level offsets, from the kernels.
+
+    Returns ``(idx int32 (N, Lq, H, L, P, 2), level_start int32 (L,))``.
+    """
+    _require_cuda(sampling_locations, "sampling_locations")
+    shapes = _shapes_tuple(spatial_shapes)
+    loc = _as_f32_contig(sampling_locations)
+    n, lq, heads, n_levels, n_points, _ = loc.shape
+    idx = torch.empty(loc.shape, dtype=torch.int32, device=loc.device)
+    starts = torch.empty((n_levels,), dtype=torch.int32, device=loc.device)
+    lib = _lib.load()
+    with torch.cuda.device(loc.device):
+        rc = lib.msda_b200_sample_indices(
+            _lib.i32_array([d for hw in shapes for d in hw]), loc.data_ptr(), idx.data_ptr(), starts.data_ptr(),
+            n, lq, heads, n_levels, n_points,
+            _default_coord_mode if coord_mode is None else coord_mode, _stream_ptr(loc.device))
+    _lib.check(rc, "msda_b200_sample_indices")
+    return idx, starts
+
+
+def locations_and_weights(offsets: torch.Tensor, logits: torch.Tensor, ref_points: torch.Tensor,
+                          spatial_shapes, n_heads: int, n_levels: int, n_points: int):
+    """Fused prologue (no autograd): softmax over L*P and ``ref + offsets / (W_l, H_l)``.
+
+    ms_deform_attn.py:392-393 and :412-416.  ``offsets`` ``(N, Lq, H*L*P*2)``, ``logits``
+    ``(N, Lq, H*L*P)``, ``ref_points`` ``(N, Lq, 1|L, 2)``.  Returns fp32
+    ``(locations (N, Lq, H, L, P, 2), attention (N, Lq, H, L, P))``.
+    """
+    _require_cuda(offsets, "offsets")
+    shapes = _shapes_tuple(spatial_shapes)
+    n, lq = offsets.shape[:2]
+    off, lg, ref = _as_f32_contig(offsets), _as_f32_contig(logits), _as_f32_contig(ref_points)
+    ref_levels = ref.shape[2]
+    loc = torch.empty((n, lq, n_heads, n_levels, n_points, 2), dtype=torch.float32, device=off.device)
+    att = torch.empty((n, lq, n_heads, n_levels, n_points), dtype=torch.float32, device=off.device)
+    lib = _lib.load()
+    with torch.cuda.device(off.device):
+        rc = lib.msda_b200_locations(off.data_ptr(), lg.data_ptr(), ref.data_ptr(), ref_levels,
+                                     _lib.i32_array([d for hw in shapes for d in hw]),
+                                     loc.data_ptr(), att.data_ptr(), n, lq, n_heads, n_levels, n_points,
+                                     _stream_ptr(off.device))
+    _lib.check(rc, "msda_b200_locations")
+    return loc, att

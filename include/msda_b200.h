@@ -1,0 +1,177 @@
+/*
+ * msda_b200.h -- C ABI of the B200 (sm_100a) multi-scale deformable attention
+ * sampling core.  This is the drop-in boundary for DETRPose's hot path.
+ *
+ * The reference has no FFI of its own (it is pure PyTorch); the entry points
+ * below are what a binding for this path would bind, one per reference
+ * function they replace:
+ *
+ *   msda_b200_forward   <- ms_deform_attn_core_pytorch, forward
+ *                          /root/reference/src/models/detrpose/ms_deform_attn.py:145-193
+ *                          (L x F.grid_sample :178 + cat :184 + mul/sum :192)
+ *   msda_b200_backward  <- autograd of the same function (ATen
+ *                          grid_sampler_2d_backward + mul/sum/cat backward)
+ *   msda_b200_locations <- the location/softmax prologue of MSDeformAttn.forward
+ *                          ms_deform_attn.py:392-393 (softmax over L*P) and
+ *                          :412-416 (ref + offsets / [W_l, H_l])
+ *   msda_b200_repack / msda_b200_unpack_grad
+ *                       <- the value construction of the caller,
+ *                          /root/reference/src/models/detrpose/transformer.py:1285-1286
+ *                          (permute + flatten + split), inverted: strided
+ *                          per-level views -> one channel-last pyramid
+ *   msda_b200_sample_indices
+ *                       <- the integer corner indices ATen derives inside
+ *                          grid_sampler_2d (GridSampler.h:27-35 + floor);
+ *                          exported so index parity can be tested bit-exactly
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types; every *device* pointer is
+ *     owned by the caller (PyTorch allocates and frees), the library keeps no
+ *     state between calls apart from a per-thread error string;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronises, is re-entrant and thread-safe (autograd calls
+ *     backward from worker threads);
+ *   - returns 0 on success, a negative MSDA_ERR_* for argument errors, a
+ *     positive cudaError_t for CUDA failures; never throws or aborts.
+ *     msda_b200_last_error() returns a per-thread description;
+ *   - "host" arrays are read during the call and may be freed on return.
+ *
+ * Data layout in HBM (kernel-native)
+ *   value pyramid : channel-last, element (n, s, h, c) at
+ *                   base + n*stride_n + s*stride_s + h*stride_h + c  (c contiguous),
+ *                   s = level_start[l] + y*W_l + x.  The reference's `memory`
+ *                   tensor (N, S, C) is exactly this with strides (S*C, C, Dh).
+ *   locations     : (N, Lq, H, L, P, 2) fp32 contiguous, last axis (x, y) in [0,1] units
+ *   attention     : (N, Lq, H, L, P)    fp32 contiguous
+ *   output        : (N, Lq, H*Dh) contiguous, fp32 or bf16
+ *   grad_value    : fp32 accumulation buffer (N, S, H, Dh) contiguous; the
+ *                   backward ADDS into it (caller zero-fills, or keeps
+ *                   accumulating across decoder layers that share `value`).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MSDA_API __attribute__((visibility("default")))
+#else
+#define MSDA_API
+#endif
+
+/* element types */
+#define MSDA_F32  0
+#define MSDA_BF16 1
+
+/* argument-check error codes (negative); CUDA errors are returned as positive cudaError_t */
+#define MSDA_OK              0
+#define MSDA_ERR_NULL       -1   /* a required pointer is NULL */
+#define MSDA_ERR_SHAPE      -2   /* a size is <= 0 or exceeds the supported range */
+#define MSDA_ERR_DTYPE      -3   /* unknown element type code */
+#define MSDA_ERR_DHEAD      -4   /* Dh not supported (must be a multiple of 8, 8..128) */
+#define MSDA_ERR_ALIGN      -5   /* a base pointer / stride breaks the 16-byte row alignment */
+#define MSDA_ERR_LEVELS     -6   /* L or P exceeds MSDA_MAX_LEVELS / MSDA_MAX_POINTS */
+#define MSDA_ERR_NO_DEVICE  -7   /* no sm_100 device / kernel image not loadable */
+
+#define MSDA_MAX_LEVELS 8
+#define MSDA_MAX_POINTS 16
+
+/* Rounding chain used to turn a normalised location into a pixel coordinate.
+ * UNFUSED reproduces the reference's elementwise fp32 ops one rounding per op
+ * (2*loc-1, +1, *size, -1, /2); FMA contracts "(g+1)*size - 1" into one
+ * fused multiply-add the way nvcc compiles ATen's CUDA grid sampler. */
+#define MSDA_COORD_UNFUSED 0
+#define MSDA_COORD_FMA     1
+
+MSDA_API int msda_b200_abi_version(void);
+MSDA_API const char* msda_b200_last_error(void);
+
+/* Number of SMs / name of the device the library will launch on (current device). */
+MSDA_API int msda_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Tuning knob for benchmarks: pin the forward / backward kernel variant
+ * (-1 = automatic selection, the default).  Process-wide, atomic. */
+MSDA_API int msda_b200_set_variant(int fwd_variant, int bwd_variant);
+
+/*
+ * Forward: out[n,q,h*Dh+c] = sum_{l,p} attn[n,q,h,l,p] * bilinear_zero_pad(value_l[n,h,c], loc[n,q,h,l,p])
+ *
+ * value          device, channel-last pyramid (see layout above), value_dtype
+ * value_strides  host[3]: (stride_n, stride_s, stride_h) in ELEMENTS; channel stride is 1
+ * spatial_shapes host[2*L]: (H_l, W_l); level starts are the running sum of H_l*W_l
+ */
+MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t* value_strides,
+                      const int32_t* spatial_shapes,
+                      const float* locations, const float* attention,
+                      void* out, int out_dtype,
+                      int N, int Lq, int H, int Dh, int L, int P,
+                      int coord_mode, void* stream);
+
+/*
+ * Backward of the above for all three inputs.
+ *
+ * grad_out        device (N, Lq, H*Dh) contiguous, grad_out_dtype
+ * grad_value      device fp32 (N, S, H, Dh) contiguous, ACCUMULATED into (may be NULL: skip)
+ * grad_locations  device fp32, shape of locations, overwritten (may be NULL together with grad_attention)
+ * grad_attention  device fp32, shape of attention, overwritten
+ */
+MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_t* value_strides,
+                       const int32_t* spatial_shapes,
+                       const float* locations, const float* attention,
+                       const void* grad_out, int grad_out_dtype,
+                       float* grad_value, float* grad_locations, float* grad_attention,
+                       int N, int Lq, int H, int Dh, int L, int P,
+                       int coord_mode, void* stream);
+
+/*
+ * Integer corner indices: idx[(n,q,h,l,p)] = (y0, x0) int32, the floor of the
+ * pixel coordinate, exactly as the forward/backward kernels compute it.
+ * level_start_out: optional DEVICE int32[L], receives the level offsets.
+ */
+MSDA_API int msda_b200_sample_indices(const int32_t* spatial_shapes, const float* locations,
+                             int32_t* idx_out, int32_t* level_start_out,
+                             int N, int Lq, int H, int L, int P,
+                             int coord_mode, void* stream);
+
+/*
+ * Location/softmax prologue (ms_deform_attn.py:392-393, :412-416):
+ *   attention = softmax_{L*P}(logits);  locations = ref + offsets / (W_l, H_l)
+ *
+ * offsets    device fp32 (N, Lq, H, L, P, 2)   (output of the offsets Linear)
+ * logits     device fp32 (N, Lq, H, L*P)       (output of the attention Linear)
+ * ref_points device fp32 (N, Lq, ref_levels, 2), ref_levels is 1 (broadcast) or L
+ */
+MSDA_API int msda_b200_locations(const float* offsets, const float* logits, const float* ref_points,
+                        int ref_levels, const int32_t* spatial_shapes,
+                        float* locations, float* attention,
+                        int N, int Lq, int H, int L, int P, void* stream);
+
+/*
+ * Repack the reference's per-level strided views into one channel-last pyramid.
+ *
+ * level_ptrs     host[L] of device pointers: element (nh=0, c=0, s=0) of value[l]
+ * level_strides  host[3*L]: strides of value[l] (N*H, Dh, H_l*W_l) in elements
+ * dst            device (N, S, H, Dh) contiguous, dst_dtype (conversion allowed)
+ */
+MSDA_API int msda_b200_repack(const void* const* level_ptrs, const int64_t* level_strides, int src_dtype,
+                     const int32_t* spatial_shapes, void* dst, int dst_dtype,
+                     int N, int H, int Dh, int L, void* stream);
+
+/*
+ * Inverse of repack for the gradient: fp32 channel-last (N, S, H, Dh) ->
+ * per-level (N*H, Dh, H_l*W_l) buffers with the given strides and dtype.
+ */
+MSDA_API int msda_b200_unpack_grad(const float* grad_value, const int32_t* spatial_shapes,
+                          void* const* level_ptrs, const int64_t* level_strides, int dst_dtype,
+                          int N, int H, int Dh, int L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */
