@@ -32,7 +32,7 @@ SIGNATURES = {
     "msda_b200_forward": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msda_b200_backward": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,
-                                   c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msda_b200_sample_indices": (c_int, [_I32P, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -127,16 +127,22 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
     if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16) return fail(MSDA_ERR_DTYPE, "unknown out dtype %d", out_dtype);
     if (!aligned16(out) || !aligned16(locations) || !aligned16(attention))
         return fail(MSDA_ERR_ALIGN, "locations / attention / out must be 16-byte aligned");
-    const cudaError_t e = msda::forward_flat(pb, value, value_dtype == MSDA_BF16, locations, attention, out,
-                                             out_dtype == MSDA_BF16, (cudaStream_t)stream);
+    // variant 1 (default when the shape fits): lean kernel; variant 0: flat kernel
+    const int variant = g_fwd_variant.load();
+    const bool vbf = value_dtype == MSDA_BF16;
+    const bool can_lean = msda::forward_lean_supported(pb, vbf);
+    if (variant == 1 && !can_lean) return fail(MSDA_ERR_SHAPE, "lean forward does not support this shape");
+    const cudaError_t e = (can_lean && variant != 0)
+        ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream)
+        : msda::forward_flat(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward launch");
 }
 
 MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_t* value_strides,
                        const int32_t* spatial_shapes, const float* locations, const float* attention,
-                       const void* grad_out, int grad_out_dtype, float* grad_value, float* grad_locations,
-                       float* grad_attention, int N, int Lq, int H, int Dh, int L, int P, int coord_mode,
-                       void* stream) {
+                       const void* grad_out, int grad_out_dtype, float* grad_value, int accumulate,
+                       float* grad_locations, float* grad_attention, int N, int Lq, int H, int Dh, int L, int P,
+                       int coord_mode, void* stream) {
     msda::Problem pb;
     int rc = make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, coord_mode);
     if (rc) return rc;
@@ -150,9 +156,25 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
         (grad_value && !aligned16(grad_value)) || (grad_locations && !aligned16(grad_locations)))
         return fail(MSDA_ERR_ALIGN, "backward buffers must be 16-byte aligned");
     if (!grad_value && !grad_locations) return MSDA_OK;
-    const cudaError_t e = msda::backward_flat(pb, value, value_dtype == MSDA_BF16, locations, attention, grad_out,
-                                              grad_out_dtype == MSDA_BF16, grad_value, grad_locations,
-                                              grad_attention, (cudaStream_t)stream);
+    const cudaStream_t st = (cudaStream_t)stream;
+    const bool vbf = value_dtype == MSDA_BF16;
+    // variant 1 (default when the shape fits): gather form, no atomics; variant 0: flat + vector reductions
+    const int variant = g_bwd_variant.load();
+    const bool can_gather = grad_out_dtype == value_dtype && msda::backward_gather_supported(pb, vbf);
+    if (variant == 1 && !can_gather)
+        return fail(MSDA_ERR_SHAPE, "gather-form backward does not support this shape/dtype combination");
+    cudaError_t e;
+    if (can_gather && variant != 0) {
+        e = msda::backward_gather(pb, value, vbf, locations, attention, grad_out, grad_value, grad_locations,
+                                  grad_attention, accumulate, st);
+    } else {
+        if (grad_value && !accumulate) {
+            e = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * pb.S * H * Dh, st);
+            if (e != cudaSuccess) return cuda_fail(e, "msda_b200_backward memset");
+        }
+        e = msda::backward_flat(pb, value, vbf, locations, attention, grad_out, grad_out_dtype == MSDA_BF16,
+                                grad_value, grad_locations, grad_attention, st);
+    }
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_backward launch");
 }
 

@@ -102,6 +102,203 @@ fwd_flat_kernel(const Problem pb, const char* __restrict__ value,
     }
 }
 
+// ---------------------------------------------------------------------------
+// Variant 1 ("lean"): same item/lane mapping, but the per-sample arithmetic is
+// done ONCE per sample instead of once per lane: phase 1 walks the CTA's
+// samples with fully coalesced loads of locations / attention (the CTA's items
+// are consecutive, so its samples are one contiguous range) and leaves
+// {4 corner weights * attention, 4 row byte offsets} in shared memory; phase 2
+// is the gather + FFMA2 accumulation, reading two 16-byte parameter vectors
+// per sample.  The instruction count per lane-sample drops ~2.5x, which is
+// what bounds this kernel (ncu: issue-bound, DRAM traffic == algorithmic).
+// ---------------------------------------------------------------------------
+struct __align__(16) SampleParams {
+    float w[4];          // nw, ne, sw, se weight times attention, 0 for dropped corners
+    uint32_t off[4];     // byte offset of the corner row from the (n, h) base; ~0u: dropped corner
+};
+
+template <int G, int K, bool VBF, bool OBF>
+__global__ void __launch_bounds__(kFwdThreads, 4)
+fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
+                const float* __restrict__ loc, const float* __restrict__ attn,
+                char* __restrict__ out) {
+    constexpr int E = Vec<VBF>::kElems;
+    constexpr int E2 = E / 2;
+    constexpr int ES = VBF ? 2 : 4;
+    constexpr int IPC = kFwdThreads / G;             // items per CTA
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int LP = pb.L * pb.P;
+    const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
+    const int64_t item0 = (int64_t)blockIdx.x * IPC;
+    const int nitems = (int)min((int64_t)IPC, items - item0);
+    const uint32_t row_bytes = (uint32_t)(pb.vs_s * ES);
+
+    // ---- phase 1: one thread per sample ----
+    // An item's parameters take LP*32 + 16 bytes: the 16-byte pad staggers the items of a warp
+    // over the banks (LP*32 alone is a multiple of 128 for the model shapes: 8-way conflicts).
+    const int item_stride = LP * 32 + 16;
+    {
+        const int nsamp = nitems * LP;
+        const float2* lsrc = reinterpret_cast<const float2*>(loc) + item0 * LP;
+        const float* asrc = attn + item0 * LP;
+        int il = tid / LP, sl = tid - il * LP;       // item inside the CTA, sample inside the item
+        const int dil = kFwdThreads / LP, dsl = kFwdThreads - dil * LP;
+        for (int s = tid; s < nsamp; s += kFwdThreads) {
+            const float2 xy = __ldg(lsrc + s);
+            const float a = __ldg(asrc + s);
+            const int l = sl / pb.P;
+            const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
+            const Sample sm = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
+            const int xc0 = min(max(sm.x0, 0), Wl - 1), xc1 = min(max(sm.x0 + 1, 0), Wl - 1);
+            const int yc0 = min(max(sm.y0, 0), Hl - 1), yc1 = min(max(sm.y0 + 1, 0), Hl - 1);
+            const uint32_t r0 = (uint32_t)(pb.geom.start[l] + yc0 * Wl), r1 = (uint32_t)(pb.geom.start[l] + yc1 * Wl);
+            unsigned char* dst = smem_raw + il * item_stride + sl * 32;
+            reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(
+                (sm.vx0 && sm.vy0) ? (r0 + xc0) * row_bytes : 0xffffffffu,
+                (sm.vx1 && sm.vy0) ? (r0 + xc1) * row_bytes : 0xffffffffu,
+                (sm.vx0 && sm.vy1) ? (r1 + xc0) * row_bytes : 0xffffffffu,
+                (sm.vx1 && sm.vy1) ? (r1 + xc1) * row_bytes : 0xffffffffu);
+            il += dil; sl += dsl;
+            if (sl >= LP) { sl -= LP; ++il; }
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: G lanes per item gather and accumulate ----
+    const int lane = tid % G;
+    const int il = tid / G;
+    if (il >= nitems) return;
+    const int64_t item = item0 + il;
+    const int h = (int)(item % pb.H);
+    const int n = (int)(item / ((int64_t)pb.H * pb.Lq));
+    const char* vbase = value + ((int64_t)n * pb.vs_n + (int64_t)h * pb.vs_h + lane * E) * ES;
+
+    float2 acc[K * E2];
+#pragma unroll
+    for (int c = 0; c < K * E2; ++c) acc[c] = make_float2(0.0f, 0.0f);
+
+    const unsigned char* ip = smem_raw + il * item_stride;
+    // B samples per step: all of their 4*K*B row loads are issued before the first use, so that every
+    // thread keeps 8 (K == 1) independent 16-byte loads in flight -- the kernel is latency-bound otherwise
+    constexpr int B = K == 1 ? 2 : 1;
+    for (int s = 0; s < LP; s += B) {
+        float wv[B][4];
+        uint4 raw[B][K][4];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const bool live = s + b < LP;
+            const float4 w = live ? reinterpret_cast<const float4*>(ip + (s + b) * 32)[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint4 o = live ? reinterpret_cast<const uint4*>(ip + (s + b) * 32)[1]
+                                 : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            wv[b][0] = w.x; wv[b][1] = w.y; wv[b][2] = w.z; wv[b][3] = w.w;
+            const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    raw[b][k][c] = ov[c] != 0xffffffffu ? ldg_nc_v4(vbase + ov[c] + k * G * 16)
+                                                        : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float2 f[E2];
+                    const uint4 r = raw[b][k][c];
+                    if constexpr (VBF) {
+                        f[0] = make_float2(bf16_lo(r.x), bf16_hi(r.x));
+                        f[1] = make_float2(bf16_lo(r.y), bf16_hi(r.y));
+                        f[2] = make_float2(bf16_lo(r.z), bf16_hi(r.z));
+                        f[3] = make_float2(bf16_lo(r.w), bf16_hi(r.w));
+                    } else {
+                        f[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
+                        f[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
+                    }
+                    const float2 ww = make_float2(wv[b][c], wv[b][c]);
+#pragma unroll
+                    for (int e = 0; e < E2; ++e) acc[k * E2 + e] = __ffma2_rn(f[e], ww, acc[k * E2 + e]);
+                }
+    }
+
+    constexpr int OS = OBF ? 2 : 4;
+    char* obase = out + (item * pb.Dh + lane * E) * OS;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        char* o = obase + k * G * E * OS;
+        const float2* a2 = acc + k * E2;
+        if constexpr (OBF) {
+            if constexpr (E == 8) {
+                uint4 v;
+                v.x = pack_bf16x2(a2[0].x, a2[0].y); v.y = pack_bf16x2(a2[1].x, a2[1].y);
+                v.z = pack_bf16x2(a2[2].x, a2[2].y); v.w = pack_bf16x2(a2[3].x, a2[3].y);
+                *reinterpret_cast<uint4*>(o) = v;
+            } else {
+                uint2 v;
+                v.x = pack_bf16x2(a2[0].x, a2[0].y); v.y = pack_bf16x2(a2[1].x, a2[1].y);
+                *reinterpret_cast<uint2*>(o) = v;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E2; e += 2)
+                *reinterpret_cast<float4*>(o + e * 8) = make_float4(a2[e].x, a2[e].y, a2[e + 1].x, a2[e + 1].y);
+        }
+    }
+}
+
+template <int G, int K, bool VBF>
+static cudaError_t launch_lean(const Problem& pb, const void* value, const float* loc, const float* attn,
+                               void* out, bool out_bf16, cudaStream_t st) {
+    constexpr int IPC = kFwdThreads / G;
+    const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
+    const unsigned grid = (unsigned)((items + IPC - 1) / IPC);
+    const size_t smem = (size_t)IPC * (pb.L * pb.P * sizeof(SampleParams) + 16);
+    auto launch = [&](auto kern) -> cudaError_t {
+        if (smem > 48 * 1024) {
+            const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out);
+        return cudaGetLastError();
+    };
+    return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true>) : launch(fwd_lean_kernel<G, K, VBF, false>);
+}
+
+// The lean kernel needs 32-bit row offsets and its parameter table in shared memory.
+bool forward_lean_supported(const Problem& pb, bool value_bf16) {
+    const int es = value_bf16 ? 2 : 4;
+    const int nv = pb.Dh * es / 16;
+    if (!(nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16)) return false;
+    if ((int64_t)pb.S * pb.vs_s * es >= (int64_t)0x7fffffff) return false;
+    const int g = nv == 3 ? 1 : nv == 6 ? 2 : nv == 12 ? 4 : nv == 16 ? 8 : nv;
+    return (size_t)(kFwdThreads / g) * (pb.L * pb.P * sizeof(SampleParams) + 16) <= 96 * 1024;
+}
+
+cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                         const float* attn, void* out, bool out_bf16, cudaStream_t st) {
+    const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
+#define MSDA_LEAN_CASE(NV, G, K)                                                          \
+    case NV:                                                                              \
+        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, st)  \
+                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, st);
+    switch (nv) {
+        MSDA_LEAN_CASE(1, 1, 1)
+        MSDA_LEAN_CASE(2, 2, 1)
+        MSDA_LEAN_CASE(3, 1, 3)
+        MSDA_LEAN_CASE(4, 4, 1)
+        MSDA_LEAN_CASE(6, 2, 3)
+        MSDA_LEAN_CASE(8, 8, 1)
+        MSDA_LEAN_CASE(12, 4, 3)
+        MSDA_LEAN_CASE(16, 8, 2)
+        default: return cudaErrorInvalidValue;
+    }
+#undef MSDA_LEAN_CASE
+}
+
 template <int G, int K, bool VBF>
 static cudaError_t launch_flat(const Problem& pb, const void* value, const float* loc, const float* attn,
                                void* out, bool out_bf16, cudaStream_t st) {

@@ -12,10 +12,20 @@ constexpr int kBwdThreads = 256;
 cudaError_t forward_flat(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                          const float* attn, void* out, bool out_bf16, cudaStream_t st);
 
+bool forward_lean_supported(const Problem& pb, bool value_bf16);
+cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                         const float* attn, void* out, bool out_bf16, cudaStream_t st);
+
 // msda_bwd.cu
 cudaError_t backward_flat(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                           const float* attn, const void* grad_out, bool go_bf16, float* grad_value,
                           float* grad_loc, float* grad_attn, cudaStream_t st);
+
+// msda_bwd_gather.cu
+bool backward_gather_supported(const Problem& pb, bool value_bf16);
+cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                            const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
+                            float* grad_attn, int accumulate, cudaStream_t st);
 
 // msda_aux.cu
 cudaError_t sample_indices(const Problem& pb, const float* loc, int32_t* idx_out,

@@ -216,11 +216,15 @@ def _forward_raw(pyramid, shapes, loc, attn, out_dtype, coord_mode):
     return out
 
 
-def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, coord_mode):
+def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, coord_mode, into=None):
+    """``into``: optional fp32 (N, S, H, Dh) buffer to ADD the value gradient to (layers sharing a value)."""
     n, total, n_heads, dh = pyramid.shape
     _, lq, _, n_levels, n_points, _ = loc.shape
     dev = pyramid.device
-    grad_value = torch.zeros((n, total, n_heads, dh), dtype=torch.float32, device=dev) if need_value else None
+    grad_value = None
+    if need_value:
+        grad_value = into if into is not None else torch.empty((n, total, n_heads, dh), dtype=torch.float32,
+                                                               device=dev)
     grad_loc = torch.empty_like(loc) if need_small else None
     grad_attn = torch.empty_like(attn) if need_small else None
     lib = _lib.load()
@@ -229,7 +233,7 @@ def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, 
             pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
             _lib.i32_array([d for hw in shapes for d in hw]),
             loc.data_ptr(), attn.data_ptr(), grad_out.data_ptr(), _code(grad_out.dtype),
-            grad_value.data_ptr() if need_value else None,
+            grad_value.data_ptr() if need_value else None, 1 if into is not None else 0,
             grad_loc.data_ptr() if need_small else None,
             grad_attn.data_ptr() if need_small else None,
             n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(dev))

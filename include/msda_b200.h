@@ -44,9 +44,9 @@
  *   locations     : (N, Lq, H, L, P, 2) fp32 contiguous, last axis (x, y) in [0,1] units
  *   attention     : (N, Lq, H, L, P)    fp32 contiguous
  *   output        : (N, Lq, H*Dh) contiguous, fp32 or bf16
- *   grad_value    : fp32 accumulation buffer (N, S, H, Dh) contiguous; the
- *                   backward ADDS into it (caller zero-fills, or keeps
- *                   accumulating across decoder layers that share `value`).
+ *   grad_value    : fp32 buffer (N, S, H, Dh) contiguous; the backward either
+ *                   overwrites it or adds into it (`accumulate`), so decoder
+ *                   layers that share `value` can accumulate in place.
  */
 #ifndef MSDA_B200_H_
 #define MSDA_B200_H_
@@ -117,7 +117,9 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
  * Backward of the above for all three inputs.
  *
  * grad_out        device (N, Lq, H*Dh) contiguous, grad_out_dtype
- * grad_value      device fp32 (N, S, H, Dh) contiguous, ACCUMULATED into (may be NULL: skip)
+ * grad_value      device fp32 (N, S, H, Dh) contiguous (may be NULL: skip)
+ * accumulate      0: grad_value is OVERWRITTEN (every element written, the caller does not zero-fill);
+ *                 1: the gradient is ADDED to the buffer (decoder layers sharing one `value`)
  * grad_locations  device fp32, shape of locations, overwritten (may be NULL together with grad_attention)
  * grad_attention  device fp32, shape of attention, overwritten
  */
@@ -125,7 +127,7 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
                        const int32_t* spatial_shapes,
                        const float* locations, const float* attention,
                        const void* grad_out, int grad_out_dtype,
-                       float* grad_value, float* grad_locations, float* grad_attention,
+                       float* grad_value, int accumulate, float* grad_locations, float* grad_attention,
                        int N, int Lq, int H, int Dh, int L, int P,
                        int coord_mode, void* stream);
 

@@ -82,7 +82,7 @@ def test_argument_errors_without_gpu(lib):
     assert rc == -3
     # backward: grads must come together
     rc = lib.msda_b200_backward(ctypes.c_void_p(0x1000), 0, strides, shapes, ctypes.c_void_p(0x1000),
-                                ctypes.c_void_p(0x1000), ctypes.c_void_p(0x1000), 0, None,
+                                ctypes.c_void_p(0x1000), ctypes.c_void_p(0x1000), 0, None, 0,
                                 ctypes.c_void_p(0x1000), None, 1, 1, 1, 8, 1, 1, 0, None)
     assert rc == -1
     # prologue: ref_levels must be 1 or L

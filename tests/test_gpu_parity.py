@@ -66,9 +66,18 @@ def _arbiter(case, memory=None, grad_out=None):
     return out, gm, gl, ga
 
 
+@pytest.fixture(params=[1, 0], ids=["bwd_gather", "bwd_flat"])
+def bwd_variant(request):
+    """Run under both backward kernels: 1 = gather form (default when the shape fits), 0 = flat + reductions."""
+    lib = _lib.load()
+    lib.msda_b200_set_variant(-1, request.param)
+    yield request.param
+    lib.msda_b200_set_variant(-1, -1)
+
+
 @pytest.mark.parametrize("layout", ["reference", "contiguous", "memory"])
 @pytest.mark.parametrize("name", CASES)
-def test_fp32_matches_reference_golden(name, layout):
+def test_fp32_matches_reference_golden(name, layout, bwd_variant):
     c = load_core_case(name)
     out, gm, gl, ga = _run(c, layout)
     assert out.shape == c["out_f32"].shape
@@ -84,7 +93,7 @@ def test_fp32_matches_reference_golden(name, layout):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_bf16_value_mode(name):
+def test_bf16_value_mode(name, bwd_variant):
     c = load_core_case(name)
     mem_r = torch.from_numpy(c["memory"]).bfloat16().float().numpy()
     go_r = torch.from_numpy(c["grad_out"]).bfloat16().float().numpy()
@@ -123,7 +132,7 @@ def test_indices_bit_exact_at_scale_vs_torch_ops_on_device():
 @pytest.mark.parametrize("wl,N,Lq", [("detrpose_n", 1, 1080), ("detrpose_s", 2, 1080), ("detrpose_x", 1, 1080),
                                      ("detrpose_l", 2, 1476), ("sweep4", 2, 300)])
 @pytest.mark.parametrize("degenerate", [False, True])
-def test_model_shapes_vs_reference_ops_on_device(wl, N, Lq, degenerate):
+def test_model_shapes_vs_reference_ops_on_device(wl, N, Lq, degenerate, bwd_variant):
     """Real model shapes: CUDA kernels vs the reference's op sequence (F.grid_sample path) run on the
     same device, plus the fp64 arbiter for the forward."""
     w = synthetic.WORKLOADS[wl]
@@ -180,6 +189,38 @@ def test_full_size_properties():
         inside = loc.detach().clamp(0.05, 0.95)
         ones = dp.ms_deform_attn_core(torch.ones_like(mem), w["shapes"], inside, att)
         assert (ones - 1.0).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("vdt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_backward_overwrite_and_accumulate_modes(vdt, bwd_variant):
+    """DETRPose-S and -L (training length -> two query chunks) shapes.  Overwrite mode needs no zero-fill
+    (the buffer starts as NaN); accumulate mode adds: two layers sharing a value give 2x the gradient.
+    fp32 results are also held against the reference's op sequence on the device."""
+    from detrpose_b200 import functional as MF
+    for wl, N, Lq in (("detrpose_s", 2, 1080), ("detrpose_l", 1, 1800)):
+        w = synthetic.WORKLOADS[wl]
+        inp = synthetic.make_inputs(N, Lq, w["H"], w["Dh"], w["shapes"], w["P"], seed=4, device=DEV, value_dtype=vdt)
+        pyr = MF.pack_value(inp["memory"], w["shapes"], w["H"])
+        cm = MF.get_default_coord_mode()
+        args = (pyr, inp["shapes"], inp["locations"], inp["attention"], inp["grad_out"], True, True, cm)
+        gv1, gl1, ga1 = MF._backward_raw(*args)
+        acc = torch.zeros_like(gv1)
+        MF._backward_raw(*args, into=acc)
+        MF._backward_raw(*args, into=acc)
+        assert torch.isfinite(gv1).all()
+        assert rel_err(acc.cpu().numpy(), 2.0 * gv1.cpu().numpy()) <= TOL
+        if vdt is torch.float32:
+            mem = inp["memory"].requires_grad_(True)
+            loc = inp["locations"].requires_grad_(True)
+            att = inp["attention"].requires_grad_(True)
+            ref_out = otorch.core(otorch.make_value_list(mem, w["H"], w["shapes"]), w["shapes"], loc, att)
+            rg = torch.autograd.grad(ref_out, [mem, loc, att], inp["grad_out"])
+            ia, _ = dp.sample_indices(loc.detach(), w["shapes"], coord_mode=_lib.COORD_UNFUSED)
+            ib, _ = dp.sample_indices(loc.detach(), w["shapes"], coord_mode=_lib.COORD_FMA)
+            keep = (ia == ib).all(-1, keepdim=True).float()
+            assert rel_err(gv1.reshape(rg[0].shape).cpu().numpy(), rg[0].cpu().numpy()) <= TOL
+            assert rel_err((gl1 * keep).cpu().numpy(), (rg[1] * keep).cpu().numpy()) <= TOL
+            assert rel_err(ga1.cpu().numpy(), rg[2].cpu().numpy()) <= TOL
 
 
 def test_repack_cache_never_serves_stale_values():
