@@ -29,6 +29,7 @@ SIGNATURES = {
     "msda_b200_last_error": (c_char_p, []),
     "msda_b200_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "msda_b200_set_variant": (c_int, [c_int, c_int]),
+    "msda_b200_debug_phase_buffer": (c_int, [c_void_p]),
     "msda_b200_forward": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,
                                   c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msda_b200_backward": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,

@@ -26,6 +26,14 @@
 
 namespace msda {
 
+// Diagnostic: when set (msda_b200_debug_phase_buffer), every CTA of the gather backward records
+// clock64() at its phase boundaries (first query chunk only): slot blockIdx.x * 8 + phase.
+__device__ unsigned long long* g_phase_buf = nullptr;
+
+cudaError_t set_phase_buffer(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(g_phase_buf, &buf, sizeof(buf));
+}
+
 namespace {
 
 constexpr int kMaxSmem = 227 * 1024;
@@ -73,6 +81,39 @@ __device__ __forceinline__ void unpack2(const uint4& v, float2* f) {     // 16 b
     }
 }
 
+// Explicit shared-space accesses on 32-bit addresses: keeps generic->shared conversions out of the
+// hot loops.  volatile keeps their order relative to the barriers; ptxas still schedules them freely.
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ unsigned lds_u16(uint32_t a) {
+    unsigned short r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(PENDING) : "memory"); }
+
 template <int G, int K, bool VBF, int THREADS, bool SMALL>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float* __restrict__ loc,
@@ -106,15 +147,18 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const int row_bytes = pb.Dh * ES;
 
     const SmemLayout lay(q_chunk, P, row_bytes, bins_words_max);
-    uint4* g_s = reinterpret_cast<uint4*>(smem + lay.off_g);
     float4* rec_s = reinterpret_cast<float4*>(smem + lay.off_rec);
     float* dots_s = reinterpret_cast<float*>(smem + lay.off_dots);
     float4* tmp_s = reinterpret_cast<float4*>(smem + lay.off_dots);      // unsorted records live here until P4
     unsigned* bins = reinterpret_cast<unsigned*>(smem + lay.off_bins);
-    const unsigned short* ends16 = reinterpret_cast<const unsigned short*>(bins);
     unsigned* scan_s = reinterpret_cast<unsigned*>(smem + lay.off_scan);
     unsigned char* order_s = smem + lay.off_order + warp * 32;           // lane holding the pixel of rank r
     int* work_s = reinterpret_cast<int*>(smem + lay.off_order + 32 * 32);
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t a_g = sbase + lay.off_g + lane * 16;                  // this lane's vector of g row 0
+    const uint32_t a_rec = sbase + lay.off_rec;
+    const uint32_t a_dots = sbase + lay.off_dots;
+    const uint32_t a_ends = sbase + lay.off_bins;
 
     const char* vlevel = value + ((int64_t)n * pb.vs_n + (int64_t)pb.geom.start[l] * pb.vs_s +
                                   (int64_t)h * pb.vs_h + lane * E) * ES;
@@ -126,48 +170,120 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const int npix = Hl * Wl;
     const float inv_w = 1.0f / (float)Wl;
     const float fW = (float)Wl, fH = (float)Hl;
+    // (q, p) of sample tid and the step to sample tid + THREADS
+    const int q_t0 = tid / P, p_t0 = tid - q_t0 * P;
+    const int dq = THREADS / P, dp = THREADS - dq * P;
+
+    unsigned long long* const pbuf = g_phase_buf;
+#define MSDA_STAMP(i) do { if (pbuf != nullptr && tid == 0 && chunk == 0) pbuf[(size_t)blockIdx.x * 8 + (i)] = clock64(); } while (0)
 
     for (int q0 = 0, chunk = 0; q0 < pb.Lq; q0 += q_chunk, ++chunk) {
         const int qc = min(q_chunk, pb.Lq - q0);
         const int nsamp = qc * P;
+        MSDA_STAMP(0);
         // sample (q, p) of this head and level sits at float2/float index s0 + q * sstride + p
         const int64_t s0 = (((int64_t)n * pb.Lq + q0) * pb.H + h) * LP + l * P;
         const int64_t sstride = (int64_t)pb.H * LP;
 
-        // ---- P0: stage grad_out rows of this head, clear the counters ----
+        // ---- P0: clear the counters; stage (asynchronously) this head's grad_out rows and the level's
+        //      locations / attention, so that no phase below waits on a dependent global load ----
+        // staging area for locations (8 B/sample) and attention (4 B/sample): the sorted-record region,
+        // which is free until P3 and again after P4
+        const float2* loc_s = reinterpret_cast<const float2*>(smem + lay.off_rec);
+        const float* att_s = reinterpret_cast<const float*>(smem + lay.off_rec + nsamp * 8);
+        auto stage_samples = [&]() {
+            if ((P & 3) == 0) {
+                // a query's P samples are contiguous: 16-byte copies (2 per 4 locations, 1 per 4 weights)
+                const int vq = P / 4;                                // 16-byte attention vectors per query
+                for (int i = tid; i < qc * vq; i += THREADS) {
+                    const int q = i / vq, v = i - q * vq;
+                    const int64_t sidx = s0 + q * sstride + v * 4;
+                    const int si = q * P + v * 4;
+                    cp_async16(a_rec + si * 8, reinterpret_cast<const float2*>(loc) + sidx);
+                    cp_async16(a_rec + si * 8 + 16, reinterpret_cast<const float2*>(loc) + sidx + 2);
+                    cp_async16(a_rec + nsamp * 8 + si * 4, attn + sidx);
+                }
+            } else {
+                int q = q_t0, p = p_t0;
+                for (int i = tid; i < nsamp; i += THREADS) {
+                    const int64_t sidx = s0 + q * sstride + p;
+                    cp_async8(a_rec + i * 8, reinterpret_cast<const float2*>(loc) + sidx);
+                    cp_async4(a_rec + nsamp * 8 + i * 4, attn + sidx);
+                    q += dq; p += dp;
+                    if (p >= P) { p -= P; ++q; }
+                }
+            }
+        };
         {
+            for (int i = tid; i < nwords; i += THREADS) bins[i] = 0u;
+            if (tid == 0) work_s[0] = 0;
+            stage_samples();
+            cp_async_commit();                               // group A: locations + attention
             const char* gsrc = grad_out + (((int64_t)n * pb.Lq + q0) * pb.H * pb.Dh + (int64_t)h * pb.Dh) * ES;
             const int64_t gstride = (int64_t)pb.H * pb.Dh * ES;
             for (int i = tid; i < qc * VPR; i += THREADS) {
                 const int q = i / VPR, v = i % VPR;
-                g_s[i] = __ldg(reinterpret_cast<const uint4*>(gsrc + q * gstride + v * 16));
+                cp_async16(sbase + lay.off_g + i * 16, gsrc + q * gstride + v * 16);
             }
-            for (int i = tid; i < nwords; i += THREADS) bins[i] = 0u;
-            if (tid == 0) work_s[0] = 0;
+            cp_async_commit();                               // group B: grad_out rows, needed from P4 on
+            cp_async_wait<1>();
         }
         __syncthreads();
+        MSDA_STAMP(1);
 
         // ---- P1: one pass over the samples: build the (unsorted) record, count per base pixel ----
-        // record = {A*wy0, A*wy1, wx1, bin+1 (0: sample has no valid corner)}
+        // record = {A*wy0, A*wy1, wx1, (bin+1) | corner validity << 20}.  Samples that are not binned
+        // (no valid corner, or |A| < 1e-30 so that wy cannot be recovered from A*wy later: their
+        // contribution to grad_value / grad_locations is below 1e-30 |grad_out| and is dropped) are finished here.
         {
-            int q = tid / P, p = tid - q * P;
-            const int dq = THREADS / P, dp = THREADS - dq * P;
+            int q = q_t0, p = p_t0;
             for (int i = tid; i < nsamp; i += THREADS) {
-                const int64_t sidx = s0 + q * sstride + p;
-                const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-                const float a = __ldg(attn + sidx);
+                const float2 xy = loc_s[i];
+                const float a = att_s[i];
                 const Sample s = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
-                int b = 0;
-                if (s.x0 >= -1 && s.x0 < Wl && s.y0 >= -1 && s.y0 < Hl) {
-                    b = (s.y0 + 1) * BW + (s.x0 + 1) + 1;
+                const bool inside = s.x0 >= -1 && s.x0 < Wl && s.y0 >= -1 && s.y0 < Hl;
+                float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);     // unbinned: .w == 0
+                if (inside && !(fabsf(a) < 1e-30f)) {        // NaN weights stay on the main path (NaN out)
+                    const int b = (s.y0 + 1) * BW + (s.x0 + 1) + 1;
                     atomicAdd(&bins[b >> 1], 1u << ((b & 1) * 16));
+                    const int packed = b | ((int)s.vx0 << 20) | ((int)s.vx1 << 21) | ((int)s.vy0 << 22) | ((int)s.vy1 << 23);
+                    t = make_float4(a * s.wy0, a * s.wy1, s.wx1, __int_as_float(packed));
+                } else if (SMALL) {
+                    // rare: grad_locations is zero (A == 0 or all corners dropped); grad_attention needs the
+                    // four corner dots, gathered directly
+                    float ga = 0.0f;
+                    if (inside) {
+                        // the staged copy of grad_out may still be in flight: read the row from global
+                        const char* grow = reinterpret_cast<const char*>(grad_out) +
+                            ((((int64_t)n * pb.Lq + q0 + q) * pb.H + h) * pb.Dh) * ES;
+                        const char* vl = value + ((int64_t)n * pb.vs_n + (int64_t)pb.geom.start[l] * pb.vs_s +
+                                                  (int64_t)h * pb.vs_h) * ES;
+                        const float wk[4] = {s.w_nw, s.w_ne, s.w_sw, s.w_se};
+                        const int px[4] = {s.x0, s.x0 + 1, s.x0, s.x0 + 1};
+                        const int py[4] = {s.y0, s.y0, s.y0 + 1, s.y0 + 1};
+                        for (int k = 0; k < 4; ++k) {
+                            if (wk[k] == 0.0f || px[k] < 0 || px[k] >= Wl || py[k] < 0 || py[k] >= Hl) continue;
+                            const char* vr = vl + (int64_t)(py[k] * Wl + px[k]) * vrow;
+                            float d = 0.0f;
+                            for (int c = 0; c < pb.Dh; ++c) {
+                                const float vv = VBF ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(vr)[c])
+                                                     : reinterpret_cast<const float*>(vr)[c];
+                                const float gg = VBF ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grow)[c])
+                                                     : reinterpret_cast<const float*>(grow)[c];
+                                d = fmaf(vv, gg, d);
+                            }
+                            ga = fmaf(wk[k], d, ga);
+                        }
+                    }
+                    t.x = ga;                                // final {grad_attn, grad_loc = 0} of this sample
                 }
-                tmp_s[i] = make_float4(a * s.wy0, a * s.wy1, s.wx1, __int_as_float(b));
+                tmp_s[i] = t;
                 q += dq; p += dp;
                 if (p >= P) { p -= P; ++q; }
             }
         }
         __syncthreads();
+        MSDA_STAMP(2);
 
         // ---- P2: exclusive scan of the packed counters (in place: count -> start) ----
         {
@@ -203,26 +319,28 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
             }
         }
         __syncthreads();
+        MSDA_STAMP(3);
 
         // ---- P3: move the records into bin order (start -> end, in place) ----
-        // sorted record = {A*wy0, A*wy1, wx1, (first g vector index << 16) | sample slot}
+        // sorted record = {A*wy0, A*wy1, wx1, corner validity << 28 | query << 16 | sample slot}
         {
-            int q = tid / P;
-            const int dq = THREADS / P, dp = THREADS - dq * P;
-            int p = tid - q * P;
+            int q = q_t0, p = p_t0;
             for (int i = tid; i < nsamp; i += THREADS) {
                 float4 r = tmp_s[i];
-                const int b = __float_as_int(r.w);
-                if (b != 0) {
+                const int packed = __float_as_int(r.w);
+                if (packed != 0) {
+                    const int b = packed & 0xfffff;
                     const unsigned old = atomicAdd(&bins[b >> 1], 1u << ((b & 1) * 16));
-                    r.w = __uint_as_float(((unsigned)(q * VPR) << 16) | (unsigned)i);
+                    r.w = __uint_as_float(((unsigned)(packed >> 20) << 28) | ((unsigned)q << 16) | (unsigned)i);
                     rec_s[half_of(old, b)] = r;
                 }
                 q += dq; p += dp;
                 if (p >= P) { p -= P; ++q; }
             }
         }
+        cp_async_wait<0>();
         __syncthreads();
+        MSDA_STAMP(4);
 
         // ---- P4: pixel owners gather ----
         {
@@ -231,57 +349,74 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
             int split = 1;
             while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 16 * npix * split)) split <<= 1;
 
-            // One unit = (pixel, part).  eu = e0_up | em_up << 16, ed likewise for the lower bin row,
-            // nt = n_up | total << 16 (records in the upper row / in both rows).
-            auto process = [&](const int pix, const int part, const bool valid, const unsigned eu,
-                               const unsigned ed, const unsigned nt) {
-                const int n_up = nt & 0xffffu, total = nt >> 16;
-                const int e0_up = eu & 0xffffu, em_up = eu >> 16;
-                const int em_dn = ed >> 16;
-                const int delta_dn = (int)(ed & 0xffffu) - n_up;
+            // A unit = (pixel, part).  Packed bin bounds: eu = e0_up | em_up << 16, ed likewise for the
+            // lower bin row, nt = n_up | total << 16 (records in the upper row / in both rows).
+            struct Unit { int pix; unsigned eu, ed, nt; bool valid; };
+
+            auto bounds = [&](const int pix, unsigned& eu, unsigned& ed, unsigned& nt) {
+                int y = (int)(((float)pix + 0.5f) * inv_w);
+                int x = pix - y * Wl;
+                if (x < 0) { --y; x += Wl; } else if (x >= Wl) { ++y; x -= Wl; }   // float rounding guard
+                const uint32_t a_dn = a_ends + (y * BW + x) * 2;   // bin (x0 = x-1, y0 = y-1); next is (x0 = x)
+                const uint32_t a_up = a_dn + BW * 2;               // bin (x0 = x-1, y0 = y)
+                const unsigned e0u = lds_u16(a_up), emu = lds_u16(a_up + 2), e1u = lds_u16(a_up + 4);
+                const unsigned e0d = lds_u16(a_dn), emd = lds_u16(a_dn + 2), e1d = lds_u16(a_dn + 4);
+                eu = e0u | (emu << 16);
+                ed = e0d | (emd << 16);
+                nt = (e1u - e0u) | ((e1u - e0u + e1d - e0d) << 16);
+            };
+            // the value row of the unit's pixel (needed for the dots only), issued ahead of its use
+            auto load_v = [&](const Unit& u, const int part, uint4* raw) {
+                const bool need = SMALL && u.valid && (int)(u.nt >> 16) > part;
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    raw[k] = need ? ldg_nc_v4(vlevel + (int64_t)u.pix * vrow + k * G * 16) : make_uint4(0, 0, 0, 0);
+            };
+
+            auto run = [&](const Unit& u, const int part, const uint4* raw) {
+                const int n_up = u.nt & 0xffffu, total = u.nt >> 16;
+                const int e0_up = u.eu & 0xffffu, em_up = u.eu >> 16;
+                const int em_dn = u.ed >> 16;
+                const int delta_dn = (int)(u.ed & 0xffffu) - n_up;
                 const int mine = total > part ? (total - part + split - 1) / split : 0;
                 const int trips = __reduce_max_sync(FULL, mine);
                 if (trips == 0 && (rmw || gvlevel == nullptr)) return;
 
                 float2 v[K * E2], acc[K * E2];
 #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const uint4 raw = (SMALL && mine > 0) ? ldg_nc_v4(vlevel + (int64_t)pix * vrow + k * G * 16)
-                                                          : make_uint4(0, 0, 0, 0);
-                    unpack2<VBF>(raw, v + k * E2);
-                }
+                for (int k = 0; k < K; ++k) unpack2<VBF>(raw[k], v + k * E2);
 #pragma unroll
                 for (int c = 0; c < K * E2; ++c) acc[c] = make_float2(0.0f, 0.0f);
 
                 int j = part;
                 for (int t = 0; t < trips; t += NB) {
                     float d[NB];
-                    unsigned slot[NB];
+                    uint32_t slot[NB];
 #pragma unroll
-                    for (int u = 0; u < NB; ++u, j += split) {
-                        d[u] = 0.0f;
-                        slot[u] = 0xffffffffu;
+                    for (int b = 0; b < NB; ++b, j += split) {
+                        d[b] = 0.0f;
+                        slot[b] = 0u;
                         if (j < total) {
                             const bool up = j < n_up;
                             const int e = j + (up ? e0_up : delta_dn);
                             const bool isx1 = e < (up ? em_up : em_dn);     // sample sits one pixel to the left
-                            const float4 rec = rec_s[e];
+                            const float4 rec = lds_f4(a_rec + e * 16);
                             const float w = (up ? rec.x : rec.y) * (isx1 ? rec.z : 1.0f - rec.z);
                             const unsigned id = __float_as_uint(rec.w);
-                            slot[u] = (id & 0xffffu) * 4u + (up ? 0u : 2u) + (isx1 ? 1u : 0u);
-                            const uint4* grow = g_s + (id >> 16) + lane;
+                            slot[b] = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
+                            const uint32_t grow = a_g + ((id >> 16) & 0xfffu) * (VPR * 16);
                             float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
                                 float2 g[E2];
-                                unpack2<VBF>(grow[k * G], g);
+                                unpack2<VBF>(lds_u4(grow + k * G * 16), g);
 #pragma unroll
                                 for (int c = 0; c < E2; ++c) {
                                     if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
                                     acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
                                 }
                             }
-                            d[u] = d2.x + d2.y;
+                            d[b] = d2.x + d2.y;
                         }
                     }
                     if (SMALL) {
@@ -293,15 +428,15 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             k1 += __shfl_xor_sync(FULL, hi2 ? d[1] : d[3], 2);
                             float keep = hi1 ? k1 : k0;
                             keep += __shfl_xor_sync(FULL, hi1 ? k0 : k1, 1);
-                            const unsigned sl = hi2 ? (hi1 ? slot[3] : slot[2]) : (hi1 ? slot[1] : slot[0]);
-                            if (sl != 0xffffffffu) dots_s[sl] = keep;
+                            const uint32_t sl = hi2 ? (hi1 ? slot[3] : slot[2]) : (hi1 ? slot[1] : slot[0]);
+                            if (sl != 0u) sts_f32(sl, keep);
                         } else {
 #pragma unroll
-                            for (int u = 0; u < NB; ++u) {
-                                float x = d[u];
+                            for (int b = 0; b < NB; ++b) {
+                                float x = d[b];
 #pragma unroll
                                 for (int off = G / 2; off > 0; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
-                                if (lane == 0 && slot[u] != 0xffffffffu) dots_s[slot[u]] = x;
+                                if (lane == 0 && slot[b] != 0u) sts_f32(slot[b], x);
                             }
                         }
                     }
@@ -314,8 +449,8 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                         acc[c].y += __shfl_xor_sync(FULL, acc[c].y, off);
                     }
                 }
-                if (gvlevel != nullptr && valid && part == 0 && !(rmw && total == 0)) {
-                    float* dst = gvlevel + (int64_t)pix * gv_row;
+                if (gvlevel != nullptr && u.valid && part == 0 && !(rmw && total == 0)) {
+                    float* dst = gvlevel + (int64_t)u.pix * gv_row;
 #pragma unroll
                     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -329,34 +464,22 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 }
             };
 
-            // bin bounds of one pixel, packed (see process)
-            auto bounds = [&](const int pix, unsigned& eu, unsigned& ed, unsigned& nt) {
-                int y = (int)(((float)pix + 0.5f) * inv_w);
-                int x = pix - y * Wl;
-                if (x < 0) { --y; x += Wl; } else if (x >= Wl) { ++y; x -= Wl; }   // float rounding guard
-                const int b_dn = y * BW + x;               // bin (x0 = x-1, y0 = y-1); +1 is (x0 = x)
-                const int b_up = b_dn + BW;                // bin (x0 = x-1, y0 = y)
-                const unsigned e0u = ends16[b_up], emu = ends16[b_up + 1], e1u = ends16[b_up + 2];
-                const unsigned e0d = ends16[b_dn], emd = ends16[b_dn + 1], e1d = ends16[b_dn + 2];
-                eu = e0u | (emu << 16);
-                ed = e0d | (emd << 16);
-                nt = (e1u - e0u) | ((e1u - e0u + e1d - e0d) << 16);
-            };
-
             if (split == 1) {
                 // sparse level: warps fetch tiles of 32 pixels; each lane reads the bounds of one pixel,
                 // the pixels are ranked by record count and handed to the groups in that order, so the
                 // UPW pixels processed together carry similar work
-                const int ntiles = (npix + 31) / 32;
+                // 32 pixels per tile (one per lane), 16 when the level has fewer tiles than warps
+                const int tpx = npix >= NWARPS * 32 ? 32 : 16;
+                const int ntiles = (npix + tpx - 1) / tpx;
                 for (;;) {
                     int tile = 0;
                     if (lane32 == 0) tile = atomicAdd(&work_s[0], 1);
                     tile = __shfl_sync(FULL, tile, 0);
                     if (tile >= ntiles) break;
-                    const int mypix = tile * 32 + lane32;
+                    const int mypix = tile * tpx + lane32;
                     unsigned eu = 0, ed = 0, nt = 0;
                     int cnt = -1;
-                    if (mypix < npix) { bounds(mypix, eu, ed, nt); cnt = min(15, (int)(nt >> 16)); }
+                    if (lane32 < tpx && mypix < npix) { bounds(mypix, eu, ed, nt); cnt = min(15, (int)(nt >> 16)); }
                     const int maxc = __reduce_max_sync(FULL, cnt);
                     const unsigned lt = (1u << lane32) - 1u;
                     int base = 0;
@@ -367,14 +490,28 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     }
                     __syncwarp();
                     const int nvalid = base;
+                    auto fetch = [&](const int u0) {
+                        Unit u;
+                        const int r = u0 + gsub;
+                        u.valid = r < nvalid;
+                        const int src = u.valid ? (int)order_s[r] : 0;
+                        u.eu = __shfl_sync(FULL, eu, src);
+                        u.ed = __shfl_sync(FULL, ed, src);
+                        u.nt = __shfl_sync(FULL, nt, src);
+                        if (!u.valid) u.nt = 0u;
+                        u.pix = tile * tpx + src;
+                        return u;
+                    };
+                    Unit nxt = fetch(0);
+                    uint4 raw_nxt[K];
+                    load_v(nxt, 0, raw_nxt);
                     for (int u0 = 0; u0 < nvalid; u0 += UPW) {
-                        const int u = u0 + gsub;
-                        const bool valid = u < nvalid;
-                        const int src = valid ? (int)order_s[u] : 0;
-                        const unsigned seu = __shfl_sync(FULL, eu, src);
-                        const unsigned sed = __shfl_sync(FULL, ed, src);
-                        const unsigned snt = __shfl_sync(FULL, nt, src);
-                        process(tile * 32 + src, 0, valid, seu, sed, valid ? snt : 0u);
+                        const Unit cur = nxt;
+                        uint4 raw[K];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) raw[k] = raw_nxt[k];
+                        if (u0 + UPW < nvalid) { nxt = fetch(u0 + UPW); load_v(nxt, 0, raw_nxt); }
+                        run(cur, 0, raw);
                     }
                     __syncwarp();
                 }
@@ -386,42 +523,76 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     if (lane32 == 0) blk = atomicAdd(&work_s[0], 1);
                     blk = __shfl_sync(FULL, blk, 0);
                     if (blk >= nblocks) break;
-                    const int u = blk * UPW + gsub;
-                    const bool valid = u < units;
-                    const int pix = valid ? u / split : 0;
-                    unsigned eu = 0, ed = 0, nt = 0;
-                    if (valid) bounds(pix, eu, ed, nt);
-                    process(pix, u & (split - 1), valid, eu, ed, nt);
+                    const int ui = blk * UPW + gsub;
+                    Unit u;
+                    u.valid = ui < units;
+                    u.pix = u.valid ? ui / split : 0;
+                    u.eu = u.ed = u.nt = 0u;
+                    if (u.valid) bounds(u.pix, u.eu, u.ed, u.nt);
+                    uint4 raw[K];
+                    load_v(u, ui & (split - 1), raw);
+                    run(u, ui & (split - 1), raw);
                 }
             }
         }
         __syncthreads();
+        MSDA_STAMP(5);
 
-        // ---- P5: per-sample gradients from the four corner dots ----
+        // ---- P5: per-sample gradients from the four corner dots, walking the sorted records ----
+        // (A, wy) are recovered from A*wy0 and A*wy1 (wy0 + wy1 == 1); nothing is re-read from global.
+        // Results replace the dots in the sample's slot: {grad_attn, grad_x, grad_y, -}; unbinned samples
+        // already hold theirs (P1).  A second sweep emits them per query with 16-byte stores: the SM's
+        // write path is bound by the number of store transactions, not by bytes.
         if (SMALL) {
-            int q = tid / P, p = tid - q * P;
-            const int dq = THREADS / P, dp = THREADS - dq * P;
-            for (int i = tid; i < nsamp; i += THREADS) {
-                const int64_t sidx = s0 + q * sstride + p;
-                const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-                const float a = __ldg(attn + sidx);
-                const Sample s = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
-                const float4 dd = *reinterpret_cast<const float4*>(dots_s + i * 4);
-                const float d0 = (s.vx0 && s.vy0) ? dd.x : 0.0f;     // nw
-                const float d1 = (s.vx1 && s.vy0) ? dd.y : 0.0f;     // ne
-                const float d2 = (s.vx0 && s.vy1) ? dd.z : 0.0f;     // sw
-                const float d3 = (s.vx1 && s.vy1) ? dd.w : 0.0f;     // se
-                const float ga = s.w_nw * d0 + s.w_ne * d1 + s.w_sw * d2 + s.w_se * d3;
-                const float gx = (d1 - d0) * s.wy0 + (d3 - d2) * s.wy1;
-                const float gy = (d2 - d0) * s.wx0 + (d3 - d1) * s.wx1;
-                grad_attn[sidx] = ga;
-                reinterpret_cast<float2*>(grad_loc)[sidx] = make_float2(a * fW * gx, a * fH * gy);
-                q += dq; p += dp;
-                if (p >= P) { p -= P; ++q; }
+            const int nrec = (int)lds_u16(a_ends + nbins * 2);          // end of the last bin
+            for (int e = tid; e < nrec; e += THREADS) {
+                const float4 rec = rec_s[e];
+                const unsigned id = __float_as_uint(rec.w);
+                const int slot = id & 0xffffu;
+                const float4 dd = *reinterpret_cast<const float4*>(dots_s + slot * 4);
+                const float a = rec.x + rec.y;
+                const float wy1 = __fdividef(rec.y, a), wy0 = 1.0f - wy1;
+                const float wx1 = rec.z, wx0 = 1.0f - wx1;
+                const bool vx0 = id & (1u << 28), vx1 = id & (1u << 29), vy0 = id & (1u << 30), vy1 = id & (1u << 31);
+                const float d0 = (vx0 && vy0) ? dd.x : 0.0f;     // nw
+                const float d1 = (vx1 && vy0) ? dd.y : 0.0f;     // ne
+                const float d2 = (vx0 && vy1) ? dd.z : 0.0f;     // sw
+                const float d3 = (vx1 && vy1) ? dd.w : 0.0f;     // se
+                const float ga = wx0 * wy0 * d0 + wx1 * wy0 * d1 + wx0 * wy1 * d2 + wx1 * wy1 * d3;
+                const float gx = (d1 - d0) * wy0 + (d3 - d2) * wy1;
+                const float gy = (d2 - d0) * wx0 + (d3 - d1) * wx1;
+                *reinterpret_cast<float4*>(dots_s + slot * 4) = make_float4(ga, a * fW * gx, a * fH * gy, 0.0f);
+            }
+            __syncthreads();
+            MSDA_STAMP(7);
+            if ((P & 3) == 0) {
+                const int vq = P / 4;
+                for (int i = tid; i < qc * vq; i += THREADS) {
+                    const int q = i / vq, v = i - q * vq;
+                    const float4* r = reinterpret_cast<const float4*>(dots_s) + q * P + v * 4;
+                    const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+                    const int64_t sidx = s0 + q * sstride + v * 4;
+                    *reinterpret_cast<float4*>(grad_attn + sidx) = make_float4(r0.x, r1.x, r2.x, r3.x);
+                    float4* gl4 = reinterpret_cast<float4*>(reinterpret_cast<float2*>(grad_loc) + sidx);
+                    gl4[0] = make_float4(r0.y, r0.z, r1.y, r1.z);
+                    gl4[1] = make_float4(r2.y, r2.z, r3.y, r3.z);
+                }
+            } else {
+                int q = q_t0, p = p_t0;
+                for (int i = tid; i < nsamp; i += THREADS) {
+                    const float4 r = reinterpret_cast<const float4*>(dots_s)[i];
+                    const int64_t sidx = s0 + q * sstride + p;
+                    grad_attn[sidx] = r.x;
+                    reinterpret_cast<float2*>(grad_loc)[sidx] = make_float2(r.y, r.z);
+                    q += dq; p += dp;
+                    if (p >= P) { p -= P; ++q; }
+                }
             }
         }
         __syncthreads();
+        MSDA_STAMP(6);
     }
+#undef MSDA_STAMP
 }
 
 template <int G, int K, bool VBF, int THREADS, bool SMALL>
@@ -460,7 +631,7 @@ static bool make_plan(const Problem& pb, int row_bytes, GatherPlan& plan) {
     const int fixed = align16(plan.bins_words * 4) + 64 * 4 + 32 * 64 * 2 + 16;
     const int per_query = row_bytes + pb.P * 32;
     int qmax = (kMaxSmem - fixed) / per_query;
-    qmax = min(qmax, 65535 / pb.P);                  // u16 counters and ids
+    qmax = min(qmax, min(65535 / pb.P, 4095));       // u16 counters / sample slots, 12-bit query ids
     if (qmax < 32) return false;
     plan.n_chunks = (pb.Lq + qmax - 1) / qmax;
     plan.q_chunk = (pb.Lq + plan.n_chunks - 1) / plan.n_chunks;
@@ -478,10 +649,25 @@ bool backward_gather_supported(const Problem& pb, bool value_bf16) {
 
 cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                             const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
-                            float* grad_attn, int accumulate, cudaStream_t st) {
+                            float* grad_attn, int accumulate, bool wide_regs, cudaStream_t st) {
     GatherPlan plan;
     if (!make_plan(pb, pb.Dh * (value_bf16 ? 2 : 4), plan)) return cudaErrorInvalidValue;
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
+    if (wide_regs) {          // 512 threads x 128 registers instead of 1024 x 64
+#define MSDA_GATHER_WIDE(NV, G, K)                                                                          \
+    case NV:                                                                                                \
+        return value_bf16 ? launch_gather<G, K, true, 512>(pb, plan, value, loc, attn, grad_out, grad_value, \
+                                                           grad_loc, grad_attn, accumulate, st)             \
+                          : launch_gather<G, K, false, 512>(pb, plan, value, loc, attn, grad_out, grad_value, \
+                                                            grad_loc, grad_attn, accumulate, st);
+        switch (nv) {
+            MSDA_GATHER_WIDE(2, 2, 1)
+            MSDA_GATHER_WIDE(4, 4, 1)
+            MSDA_GATHER_WIDE(8, 8, 1)
+            default: break;
+        }
+#undef MSDA_GATHER_WIDE
+    }
 #define MSDA_GATHER_CASE(NV, G, K, T)                                                                       \
     case NV:                                                                                                \
         return value_bf16 ? launch_gather<G, K, true, T>(pb, plan, value, loc, attn, grad_out, grad_value,   \

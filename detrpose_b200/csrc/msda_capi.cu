@@ -109,6 +109,11 @@ MSDA_API int msda_b200_device_info(int* sm_count, int* cc_major, int* cc_minor) 
     return MSDA_OK;
 }
 
+MSDA_API int msda_b200_debug_phase_buffer(void* device_buffer) {
+    const cudaError_t e = msda::set_phase_buffer(static_cast<unsigned long long*>(device_buffer));
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_debug_phase_buffer");
+}
+
 MSDA_API int msda_b200_set_variant(int fwd_variant, int bwd_variant) {
     g_fwd_variant.store(fwd_variant);
     g_bwd_variant.store(bwd_variant);
@@ -158,15 +163,16 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
     if (!grad_value && !grad_locations) return MSDA_OK;
     const cudaStream_t st = (cudaStream_t)stream;
     const bool vbf = value_dtype == MSDA_BF16;
-    // variant 1 (default when the shape fits): gather form, no atomics; variant 0: flat + vector reductions
+    // variant 1 (default when the shape fits): gather form, no atomics (2: same with 512 threads x 128
+    // registers); variant 0: flat + vector reductions
     const int variant = g_bwd_variant.load();
     const bool can_gather = grad_out_dtype == value_dtype && msda::backward_gather_supported(pb, vbf);
-    if (variant == 1 && !can_gather)
+    if ((variant == 1 || variant == 2) && !can_gather)
         return fail(MSDA_ERR_SHAPE, "gather-form backward does not support this shape/dtype combination");
     cudaError_t e;
     if (can_gather && variant != 0) {
         e = msda::backward_gather(pb, value, vbf, locations, attention, grad_out, grad_value, grad_locations,
-                                  grad_attention, accumulate, st);
+                                  grad_attention, accumulate, variant == 2, st);
     } else {
         if (grad_value && !accumulate) {
             e = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * pb.S * H * Dh, st);

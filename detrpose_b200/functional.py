@@ -27,9 +27,12 @@ __all__ = [
 
 _DTYPE_CODE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
 
-# Rounding chain for the pixel coordinate (see include/msda_b200.h).  UNFUSED is the
-# reference's elementwise-op chain; tests/gpu decide which one ATen's CUDA sampler uses.
-_default_coord_mode = _lib.COORD_UNFUSED
+# Rounding chain for the pixel coordinate (see include/msda_b200.h).  On a GPU the reference runs
+# ATen's CUDA grid sampler, which nvcc compiles with "(g+1)*size - 1" contracted into one FMA
+# (tools/probe_coord_mode.py: 11 of 11 ambiguous samples in 3.2e8 agree with the FMA chain, see
+# profiles/r01_coord_chain_probe.json), so FMA is the default.  COORD_UNFUSED reproduces the
+# one-rounding-per-op chain of elementwise torch ops / the CPU oracle bit for bit.
+_default_coord_mode = _lib.COORD_FMA
 
 
 def set_default_coord_mode(mode: int) -> None:

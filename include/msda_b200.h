@@ -99,6 +99,10 @@ MSDA_API int msda_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (-1 = automatic selection, the default).  Process-wide, atomic. */
 MSDA_API int msda_b200_set_variant(int fwd_variant, int bwd_variant);
 
+/* Diagnostic: device buffer of 8 uint64 per backward CTA (N*H*L CTAs) that receives clock64()
+ * at the phase boundaries of the gather-form backward; NULL (default) disables it. */
+MSDA_API int msda_b200_debug_phase_buffer(void* device_buffer);
+
 /*
  * Forward: out[n,q,h*Dh+c] = sum_{l,p} attn[n,q,h,l,p] * bilinear_zero_pad(value_l[n,h,c], loc[n,q,h,l,p])
  *

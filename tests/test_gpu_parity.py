@@ -45,7 +45,8 @@ def _run(case, layout, value_dtype=torch.float32):
         value = mem
     else:
         raise AssertionError(layout)
-    out = dp.ms_deform_attn_core(value, shapes, loc, att)
+    # the golden vectors come from the reference on CPU, whose coordinate chain rounds every op
+    out = dp.ms_deform_attn_core(value, shapes, loc, att, coord_mode=_lib.COORD_UNFUSED)
     gm, gl, ga = torch.autograd.grad(out, [mem, loc, att], go)
     torch.cuda.synchronize()
     return [t.detach().float().cpu().numpy() for t in (out, gm, gl, ga)]
@@ -127,6 +128,23 @@ def test_indices_bit_exact_at_scale_vs_torch_ops_on_device():
         y = ((grid[:, :, :, l, :, 1] + 1) * h - 1) / 2
         assert torch.equal(idx[:, :, :, l, :, 1], torch.floor(x).clamp(-2, w + 1).int())
         assert torch.equal(idx[:, :, :, l, :, 0], torch.floor(y).clamp(-2, h + 1).int())
+
+
+def test_fma_chain_indices_bit_exact_at_scale():
+    """COORD_FMA (the default: what ATen's CUDA sampler does) against the same chain with the fused
+    multiply-subtract emulated exactly in fp64: (g+1)*size has at most 48 significant bits, so
+    fp64 holds t*size - 1 exactly and one rounding to fp32 gives fma(t, size, -1)."""
+    g = torch.Generator(device=DEV).manual_seed(6)
+    shapes = ((80, 80), (40, 40), (20, 20), (100, 75), (15, 25))
+    loc = torch.rand((8, 20000, 8, len(shapes), 16, 2), device=DEV, generator=g) * 1.2 - 0.1
+    idx, _ = dp.sample_indices(loc, shapes, coord_mode=_lib.COORD_FMA)
+    t = (2 * loc - 1) + 1
+    for l, (h, w) in enumerate(shapes):
+        x = ((t[:, :, :, l, :, 0].double() * w - 1).float()) / 2
+        y = ((t[:, :, :, l, :, 1].double() * h - 1).float()) / 2
+        assert torch.equal(idx[:, :, :, l, :, 1], torch.floor(x).clamp(-2, w + 1).int())
+        assert torch.equal(idx[:, :, :, l, :, 0], torch.floor(y).clamp(-2, h + 1).int())
+    assert dp.get_default_coord_mode() == _lib.COORD_FMA
 
 
 @pytest.mark.parametrize("wl,N,Lq", [("detrpose_n", 1, 1080), ("detrpose_s", 2, 1080), ("detrpose_x", 1, 1080),
@@ -221,6 +239,23 @@ def test_backward_overwrite_and_accumulate_modes(vdt, bwd_variant):
             assert rel_err(gv1.reshape(rg[0].shape).cpu().numpy(), rg[0].cpu().numpy()) <= TOL
             assert rel_err((gl1 * keep).cpu().numpy(), (rg[1] * keep).cpu().numpy()) <= TOL
             assert rel_err(ga1.cpu().numpy(), rg[2].cpu().numpy()) <= TOL
+
+
+def test_zero_attention_weights_and_masked_points(bwd_variant):
+    """Exact zeros in the attention weights (masked points): grad_attention of those samples still
+    needs the corner dots; grad_locations is exactly zero there."""
+    c = load_core_case("s_like")
+    att = c["attention"].copy()
+    rng = np.random.default_rng(0)
+    mask = rng.random(att.shape) < 0.3
+    att[mask] = 0.0
+    c2 = dict(c, attention=att)
+    out, gm, gl, ga = _run(c2, "reference")
+    a_out, a_gm, a_gl, a_ga = _arbiter(c2)
+    assert rel_err(out, a_out) <= TOL and rel_err(gm, a_gm) <= TOL
+    assert rel_err(gl, a_gl) <= TOL and rel_err(ga, a_ga) <= TOL
+    assert np.all(gl[mask] == 0.0)
+    assert np.abs(ga[mask]).max() > 0.0
 
 
 def test_repack_cache_never_serves_stale_values():
