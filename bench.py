@@ -155,6 +155,12 @@ def time_cpu_reference(w, dtype, images, steps, warmup):
     the same work per image."""
     from detrpose_b200 import synthetic
     from oracle import msda_torch as otorch          # checker / CPU baseline only
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores))
     inp = synthetic.make_inputs(images, w["Lq"], w["H"], w["Dh"], w["shapes"], w["P"], seed=0, device="cpu")
     value = otorch.make_value_list(inp["memory"], w["H"], w["shapes"])
     times = []
@@ -369,8 +375,10 @@ def run_b200_arm(args):
                          "algorithmic_bytes_per_launch": int(bwd_bytes)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -101,6 +101,16 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t a) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
 }
+// 256-bit global accesses (sm_100): the 4 lanes that own a pixel write its 128-byte fp32 gradient
+// row as ONE request instead of two half-line requests (the SM's request rate bounds this phase)
+__device__ __forceinline__ void stg_v8(float* p, const float2 a, const float2 b, const float2 c, const float2 d) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y) : "memory");
+}
+__device__ __forceinline__ void ldg_v8(const float* p, float2& a, float2& b, float2& c, float2& d) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y) : "l"(p));
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
@@ -167,6 +177,9 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     float* gvlevel = grad_value
         ? grad_value + ((int64_t)n * pb.S + pb.geom.start[l]) * gv_row + (int64_t)h * pb.Dh + lane * E
         : nullptr;
+    // 256-bit row stores (one request per 128-byte row) measured slower than two 128-bit stores here
+    // (602 vs 568 us at batch 64): kept behind this switch
+    constexpr bool wide_store = false;
     const int npix = Hl * Wl;
     const float inv_w = 1.0f / (float)Wl;
     const float fW = (float)Wl, fH = (float)Hl;
@@ -346,8 +359,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         {
             const bool rmw = accumulate || chunk > 0;
             // dense coarse levels: `split` groups share one pixel and take every split-th record
-            int split = 1;
-            while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 16 * npix * split)) split <<= 1;
+            int split = 1, split_log2 = 0;
+            while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 16 * npix * split)) {
+                split <<= 1;
+                ++split_log2;
+            }
 
             // A unit = (pixel, part).  Packed bin bounds: eu = e0_up | em_up << 16, ed likewise for the
             // lower bin row, nt = n_up | total << 16 (records in the upper row / in both rows).
@@ -378,7 +394,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 const int e0_up = u.eu & 0xffffu, em_up = u.eu >> 16;
                 const int em_dn = u.ed >> 16;
                 const int delta_dn = (int)(u.ed & 0xffffu) - n_up;
-                const int mine = total > part ? (total - part + split - 1) / split : 0;
+                const int mine = total > part ? (total - part + split - 1) >> split_log2 : 0;
                 const int trips = __reduce_max_sync(FULL, mine);
                 if (trips == 0 && (rmw || gvlevel == nullptr)) return;
 
@@ -389,48 +405,88 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 for (int c = 0; c < K * E2; ++c) acc[c] = make_float2(0.0f, 0.0f);
 
                 int j = part;
-                for (int t = 0; t < trips; t += NB) {
-                    float d[NB];
-                    uint32_t slot[NB];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b, j += split) {
-                        d[b] = 0.0f;
-                        slot[b] = 0u;
-                        if (j < total) {
-                            const bool up = j < n_up;
-                            const int e = j + (up ? e0_up : delta_dn);
+                if constexpr (G == 4) {
+                    // Cooperative decode: in a batch of 4 visits lane i of the group decodes visit i (record,
+                    // weight, g-row address, dot slot); weight and address are then broadcast inside the
+                    // group, and after the transpose-reduce lane i holds the dot of the visit it decoded.
+                    const uint32_t a_g0 = a_g - lane * 16;                    // g row 0, vector 0
+                    for (int t = 0; t < trips; t += 4, j += 4 * split) {
+                        const int jm = j + lane * split;
+                        float w_m = 0.0f;
+                        uint32_t ga_m = 0xffffffffu, slot_m = 0u;
+                        if (jm < total) {
+                            const bool up = jm < n_up;
+                            const int e = jm + (up ? e0_up : delta_dn);
                             const bool isx1 = e < (up ? em_up : em_dn);     // sample sits one pixel to the left
                             const float4 rec = lds_f4(a_rec + e * 16);
-                            const float w = (up ? rec.x : rec.y) * (isx1 ? rec.z : 1.0f - rec.z);
+                            w_m = (up ? rec.x : rec.y) * (isx1 ? rec.z : 1.0f - rec.z);
                             const unsigned id = __float_as_uint(rec.w);
-                            slot[b] = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
-                            const uint32_t grow = a_g + ((id >> 16) & 0xfffu) * (VPR * 16);
-                            float2 d2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                            for (int k = 0; k < K; ++k) {
-                                float2 g[E2];
-                                unpack2<VBF>(lds_u4(grow + k * G * 16), g);
-#pragma unroll
-                                for (int c = 0; c < E2; ++c) {
-                                    if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
-                                    acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
-                                }
-                            }
-                            d[b] = d2.x + d2.y;
+                            slot_m = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
+                            ga_m = a_g0 + ((id >> 16) & 0xfffu) * (VPR * 16);
                         }
-                    }
-                    if (SMALL) {
-                        if constexpr (G == 4) {
-                            // 4 visits x 4 lanes: transpose-reduce, lane i ends with the dot of visit i
+                        float d[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float w = __shfl_sync(FULL, w_m, u, 4);
+                            const uint32_t ga = __shfl_sync(FULL, ga_m, u, 4);
+                            d[u] = 0.0f;
+                            if (ga != 0xffffffffu) {
+                                float2 d2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    float2 g[E2];
+                                    unpack2<VBF>(lds_u4(ga + (k * G + lane) * 16), g);
+#pragma unroll
+                                    for (int c = 0; c < E2; ++c) {
+                                        if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
+                                        acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
+                                    }
+                                }
+                                d[u] = d2.x + d2.y;
+                            }
+                        }
+                        if (SMALL) {
                             const bool hi2 = lane & 2, hi1 = lane & 1;
                             float k0 = hi2 ? d[2] : d[0], k1 = hi2 ? d[3] : d[1];
                             k0 += __shfl_xor_sync(FULL, hi2 ? d[0] : d[2], 2);
                             k1 += __shfl_xor_sync(FULL, hi2 ? d[1] : d[3], 2);
                             float keep = hi1 ? k1 : k0;
                             keep += __shfl_xor_sync(FULL, hi1 ? k0 : k1, 1);
-                            const uint32_t sl = hi2 ? (hi1 ? slot[3] : slot[2]) : (hi1 ? slot[1] : slot[0]);
-                            if (sl != 0u) sts_f32(sl, keep);
-                        } else {
+                            if (jm < total) sts_f32(slot_m, keep);
+                        }
+                    }
+                } else {
+                    for (int t = 0; t < trips; t += NB) {
+                        float d[NB];
+                        uint32_t slot[NB];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b, j += split) {
+                            d[b] = 0.0f;
+                            slot[b] = 0u;
+                            if (j < total) {
+                                const bool up = j < n_up;
+                                const int e = j + (up ? e0_up : delta_dn);
+                                const bool isx1 = e < (up ? em_up : em_dn);     // sample sits one pixel to the left
+                                const float4 rec = lds_f4(a_rec + e * 16);
+                                const float w = (up ? rec.x : rec.y) * (isx1 ? rec.z : 1.0f - rec.z);
+                                const unsigned id = __float_as_uint(rec.w);
+                                slot[b] = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
+                                const uint32_t grow = a_g + ((id >> 16) & 0xfffu) * (VPR * 16);
+                                float2 d2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    float2 g[E2];
+                                    unpack2<VBF>(lds_u4(grow + k * G * 16), g);
+#pragma unroll
+                                    for (int c = 0; c < E2; ++c) {
+                                        if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
+                                        acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
+                                    }
+                                }
+                                d[b] = d2.x + d2.y;
+                            }
+                        }
+                        if (SMALL) {
 #pragma unroll
                             for (int b = 0; b < NB; ++b) {
                                 float x = d[b];
@@ -451,6 +507,19 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 }
                 if (gvlevel != nullptr && u.valid && part == 0 && !(rmw && total == 0)) {
                     float* dst = gvlevel + (int64_t)u.pix * gv_row;
+                    if (E == 8 && wide_store) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            float2* a2 = acc + k * E2;
+                            if (rmw) {
+                                float2 t0, t1, t2, t3;
+                                ldg_v8(dst + k * G * E, t0, t1, t2, t3);
+                                a2[0].x += t0.x; a2[0].y += t0.y; a2[1].x += t1.x; a2[1].y += t1.y;
+                                a2[2].x += t2.x; a2[2].y += t2.y; a2[3].x += t3.x; a2[3].y += t3.y;
+                            }
+                            stg_v8(dst + k * G * E, a2[0], a2[1], a2[2], a2[3]);
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -526,7 +595,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     const int ui = blk * UPW + gsub;
                     Unit u;
                     u.valid = ui < units;
-                    u.pix = u.valid ? ui / split : 0;
+                    u.pix = u.valid ? ui >> split_log2 : 0;
                     u.eu = u.ed = u.nt = 0u;
                     if (u.valid) bounds(u.pix, u.eu, u.ed, u.nt);
                     uint4 raw[K];

@@ -137,9 +137,16 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
     const bool vbf = value_dtype == MSDA_BF16;
     const bool can_lean = msda::forward_lean_supported(pb, vbf);
     if (variant == 1 && !can_lean) return fail(MSDA_ERR_SHAPE, "lean forward does not support this shape");
-    const cudaError_t e = (can_lean && variant != 0)
-        ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream)
-        : msda::forward_flat(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
+    cudaError_t e;
+    if (variant == 2) {            // TMA-staged coarse levels (opt-in until it wins across shapes)
+        if (!msda::forward_staged_supported(pb, vbf))
+            return fail(MSDA_ERR_SHAPE, "staged forward does not support this shape");
+        e = msda::forward_staged(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
+    } else {
+        e = (can_lean && variant != 0)
+            ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream)
+            : msda::forward_flat(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
+    }
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward launch");
 }
 

@@ -28,6 +28,16 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_call(item):
+    """A kernel variant forced by the `bwd_variant` fixture refuses shapes it does not support
+    (the library fails loudly instead of falling back): report those combinations as skipped."""
+    outcome = yield
+    if outcome.excinfo is not None and "bwd_variant" in getattr(item, "fixturenames", ()):
+        if "does not support this shape" in str(outcome.excinfo[1]):
+            outcome.force_exception(pytest.skip.Exception(str(outcome.excinfo[1])))
+
+
 def core_case_names():
     return sorted(os.path.basename(p)[len("core_"):-len(".npz")]
                   for p in glob.glob(os.path.join(GOLDEN_DIR, "core_*.npz")))

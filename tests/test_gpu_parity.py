@@ -67,11 +67,13 @@ def _arbiter(case, memory=None, grad_out=None):
     return out, gm, gl, ga
 
 
-@pytest.fixture(params=[1, 0], ids=["bwd_gather", "bwd_flat"])
+@pytest.fixture(params=[(1, 1), (0, 0), (2, 1)], ids=["lean+gather", "flat+flat", "staged+gather"])
 def bwd_variant(request):
-    """Run under both backward kernels: 1 = gather form (default when the shape fits), 0 = flat + reductions."""
+    """Run under every kernel variant.  Forward: 1 = lean (default), 0 = flat, 2 = TMA-staged coarse levels;
+    backward: 1 = gather form (default when the shape fits), 0 = flat + vector reductions.  A forced
+    variant that does not support a shape fails loudly in the library; those combinations are skipped."""
     lib = _lib.load()
-    lib.msda_b200_set_variant(-1, request.param)
+    lib.msda_b200_set_variant(*request.param)
     yield request.param
     lib.msda_b200_set_variant(-1, -1)
 
