@@ -144,9 +144,23 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const int tid = threadIdx.x;
     const int lane = tid % G;
     const int lane32 = tid & 31, warp = tid >> 5, gsub = lane32 / G;
-    const int l = blockIdx.x % pb.L;
-    const int h = (blockIdx.x / pb.L) % pb.H;
-    const int n = blockIdx.x / (pb.L * pb.H);
+    // CTA -> (image, head, level).  The levels of one (image, head) sit next to each other so that they
+    // share grad_out / locations / attention in L2; only in the tail of the grid (the last kTail pairs)
+    // the long finest-level CTAs are issued first, so that the last CTAs to start are the short ones.
+    int l, nh;
+    {
+        constexpr int kTail = 148;
+        const int NH = pb.N * pb.H, b = blockIdx.x;
+        const int head_ctas = max(NH - kTail, 0) * pb.L;
+        if (b < head_ctas || pb.L == 1) { nh = b / pb.L; l = b - nh * pb.L; }
+        else {
+            const int r = b - head_ctas, t = NH - head_ctas / pb.L;       // t pairs in the tail
+            if (r < t) { nh = head_ctas / pb.L + r; l = 0; }
+            else { const int r2 = r - t; nh = head_ctas / pb.L + r2 / (pb.L - 1); l = 1 + r2 % (pb.L - 1); }
+        }
+    }
+    const int h = nh % pb.H;
+    const int n = nh / pb.H;
     const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
     const int BW = Wl + 1;                           // bins per row: x0 in [-1, W-1]
     const int nbins = BW * (Hl + 1);

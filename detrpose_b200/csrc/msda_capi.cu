@@ -138,10 +138,12 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
     const bool can_lean = msda::forward_lean_supported(pb, vbf);
     if (variant == 1 && !can_lean) return fail(MSDA_ERR_SHAPE, "lean forward does not support this shape");
     cudaError_t e;
-    if (variant == 2) {            // TMA-staged coarse levels (opt-in until it wins across shapes)
-        if (!msda::forward_staged_supported(pb, vbf))
+    if (variant == 2 || variant == 3) {   // TMA-staged coarse levels (opt-in): 2 = one 768-thread CTA per SM
+        const bool small = variant == 3;  // staging all it can, 3 = 256-thread CTAs staging the coarsest level(s)
+        if (!msda::forward_staged_supported(pb, vbf, small))
             return fail(MSDA_ERR_SHAPE, "staged forward does not support this shape");
-        e = msda::forward_staged(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
+        e = msda::forward_staged(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, small,
+                                 (cudaStream_t)stream);
     } else {
         e = (can_lean && variant != 0)
             ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream)

@@ -170,7 +170,9 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     // ---- phase 2: G lanes per item gather and accumulate ----
     const int lane = tid % G;
     const int il = tid / G;
-    if (il >= nitems) return;
+    // rows that are not a power-of-two number of 16-byte vectors (Dh = 48 bf16: 6) use the next power of
+    // two of lanes with the surplus lanes idle: one request per corner row instead of three
+    if (il >= nitems || lane * 16 >= pb.Dh * ES) return;
     const int64_t item = item0 + il;
     const int h = (int)(item % pb.H);
     const int n = (int)(item / ((int64_t)pb.H * pb.Lq));
@@ -274,7 +276,7 @@ bool forward_lean_supported(const Problem& pb, bool value_bf16) {
     const int nv = pb.Dh * es / 16;
     if (!(nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16)) return false;
     if ((int64_t)pb.S * pb.vs_s * es >= (int64_t)0x7fffffff) return false;
-    const int g = nv == 3 ? 1 : nv == 6 ? 2 : nv == 12 ? 4 : nv == 16 ? 8 : nv;
+    const int g = nv == 3 ? 1 : nv == 6 ? 8 : nv == 12 ? 4 : nv == 16 ? 8 : nv;
     return (size_t)(kFwdThreads / g) * (pb.L * pb.P * sizeof(SampleParams) + 16) <= 96 * 1024;
 }
 
@@ -290,7 +292,7 @@ cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, 
         MSDA_LEAN_CASE(2, 2, 1)
         MSDA_LEAN_CASE(3, 1, 3)
         MSDA_LEAN_CASE(4, 4, 1)
-        MSDA_LEAN_CASE(6, 2, 3)
+        MSDA_LEAN_CASE(6, 8, 1)
         MSDA_LEAN_CASE(8, 8, 1)
         MSDA_LEAN_CASE(12, 4, 3)
         MSDA_LEAN_CASE(16, 8, 2)

@@ -14,7 +14,6 @@ namespace msda {
 
 namespace {
 
-constexpr int kStagedThreads = 768;
 constexpr int kBoxRows = 64;                 // pixel rows per TMA box
 constexpr int kMaxSmemStaged = 227 * 1024;
 
@@ -57,8 +56,8 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 
 }  // namespace
 
-template <int G, int K, bool VBF, bool OBF>
-__global__ void __launch_bounds__(kStagedThreads, 1)
+template <int G, int K, bool VBF, bool OBF, int kStagedThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kStagedThreads, kMinBlocks)
 fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, const StagePlan plan,
                   const char* __restrict__ value, const float* __restrict__ loc,
                   const float* __restrict__ attn, char* __restrict__ out) {
@@ -238,12 +237,15 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-bool make_stage_plan(const Problem& pb, bool value_bf16, int G, StagePlan& plan) {
+// `small`: 256-thread CTAs that stage only what fits beside three co-resident CTAs (the coarsest
+// level for the DETRPose shapes) instead of one 768-thread CTA per SM staging everything it can.
+bool make_stage_plan(const Problem& pb, bool value_bf16, int G, bool small, StagePlan& plan) {
     const int es = value_bf16 ? 2 : 4;
     const int srow = pb.Dh * es;
-    const int ipc = kStagedThreads / G;
+    const int threads = small ? 256 : 768;
+    const int ipc = threads / G;
     const int params_bytes = ipc * (pb.L * pb.P * 32 + 16) + 16;
-    const int budget = kMaxSmemStaged - params_bytes - 256;
+    const int budget = (small ? kMaxSmemStaged / 4 : kMaxSmemStaged) - params_bytes - 256;
     // stage the longest suffix of levels that fits
     int first = pb.L, bytes = 0;
     for (int l = pb.L - 1; l >= 0; --l) {
@@ -266,34 +268,47 @@ bool make_stage_plan(const Problem& pb, bool value_bf16, int G, StagePlan& plan)
     }
     plan.stage_bytes = off;                      // multiple of kBoxRows * srow (>= 1 KB): keeps 128-byte alignment
     plan.n_boxes = boxes;
-    // enough CTAs for ~4 waves of 148 SMs, but at least one full pass of queries per CTA
-    int parts = 1;
-    while ((int64_t)pb.N * pb.H * parts < 592 && pb.Lq / (parts * 2) >= ipc) parts *= 2;
-    plan.parts = parts;
-    plan.q_per_part = (pb.Lq + parts - 1) / parts;
+    if (small) {             // one pass of queries per CTA
+        plan.parts = (pb.Lq + ipc - 1) / ipc;
+        plan.q_per_part = ipc;
+    } else {                 // enough CTAs for ~4 waves of 148 SMs, but at least one full pass per CTA
+        int parts = 1;
+        while ((int64_t)pb.N * pb.H * parts < 592 && pb.Lq / (parts * 2) >= ipc) parts *= 2;
+        plan.parts = parts;
+        plan.q_per_part = (pb.Lq + parts - 1) / parts;
+    }
     return true;
 }
 
-template <int G, int K, bool VBF>
-cudaError_t launch_staged(const Problem& pb, const StagePlan& plan, const CUtensorMap& tmap, const void* value,
-                          const float* loc, const float* attn, void* out, bool out_bf16, cudaStream_t st) {
-    constexpr int IPC = kStagedThreads / G;
+template <int G, int K, bool VBF, int THREADS, int MINB>
+cudaError_t launch_staged_t(const Problem& pb, const StagePlan& plan, const CUtensorMap& tmap, const void* value,
+                            const float* loc, const float* attn, void* out, bool out_bf16, cudaStream_t st) {
+    constexpr int IPC = THREADS / G;
     const size_t smem = (size_t)plan.stage_bytes + (size_t)IPC * (pb.L * pb.P * 32 + 16) + 16;
     const unsigned grid = (unsigned)(pb.N * pb.H * plan.parts);
     auto launch = [&](auto kern) -> cudaError_t {
         const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemStaged);
         if (e != cudaSuccess) return e;
-        kern<<<grid, kStagedThreads, smem, st>>>(tmap, pb, plan, (const char*)value, loc, attn, (char*)out);
+        kern<<<grid, THREADS, smem, st>>>(tmap, pb, plan, (const char*)value, loc, attn, (char*)out);
         return cudaGetLastError();
     };
-    return out_bf16 ? launch(fwd_staged_kernel<G, K, VBF, true>) : launch(fwd_staged_kernel<G, K, VBF, false>);
+    return out_bf16 ? launch(fwd_staged_kernel<G, K, VBF, true, THREADS, MINB>)
+                    : launch(fwd_staged_kernel<G, K, VBF, false, THREADS, MINB>);
+}
+
+template <int G, int K, bool VBF>
+cudaError_t launch_staged(const Problem& pb, const StagePlan& plan, bool small, const CUtensorMap& tmap,
+                          const void* value, const float* loc, const float* attn, void* out, bool out_bf16,
+                          cudaStream_t st) {
+    return small ? launch_staged_t<G, K, VBF, 256, 4>(pb, plan, tmap, value, loc, attn, out, out_bf16, st)
+                 : launch_staged_t<G, K, VBF, 768, 1>(pb, plan, tmap, value, loc, attn, out, out_bf16, st);
 }
 
 int lanes_for(int nv) { return nv == 3 ? 1 : nv == 6 ? 2 : nv == 12 ? 4 : nv == 16 ? 8 : nv; }
 
 }  // namespace
 
-bool forward_staged_supported(const Problem& pb, bool value_bf16) {
+bool forward_staged_supported(const Problem& pb, bool value_bf16, bool small) {
     const int es = value_bf16 ? 2 : 4;
     const int nv = pb.Dh * es / 16;
     if (!(nv == 2 || nv == 4 || nv == 6 || nv == 8)) return false;
@@ -301,15 +316,15 @@ bool forward_staged_supported(const Problem& pb, bool value_bf16) {
     if ((int64_t)pb.S * pb.vs_s * es >= (int64_t)0x7fffffff) return false;
     if (pb.Dh > 256 || pb.S < 1) return false;
     StagePlan plan;
-    return make_stage_plan(pb, value_bf16, lanes_for(nv), plan);
+    return make_stage_plan(pb, value_bf16, lanes_for(nv), small, plan);
 }
 
 cudaError_t forward_staged(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                           const float* attn, void* out, bool out_bf16, cudaStream_t st) {
+                           const float* attn, void* out, bool out_bf16, bool small, cudaStream_t st) {
     const int es = value_bf16 ? 2 : 4;
     const int nv = pb.Dh * es / 16;
     StagePlan plan;
-    if (!make_stage_plan(pb, value_bf16, lanes_for(nv), plan)) return cudaErrorInvalidValue;
+    if (!make_stage_plan(pb, value_bf16, lanes_for(nv), small, plan)) return cudaErrorInvalidValue;
     // 4-D tensor map of the strided pyramid: (channel, head, pixel, image)
     CUtensorMap tmap;
     const cuuint64_t dims[4] = {(cuuint64_t)pb.Dh, (cuuint64_t)pb.H, (cuuint64_t)pb.S, (cuuint64_t)pb.N};
@@ -325,8 +340,8 @@ cudaError_t forward_staged(const Problem& pb, const void* value, bool value_bf16
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 #define MSDA_STAGED_CASE(NV, G, K)                                                                        \
     case NV:                                                                                              \
-        return value_bf16 ? launch_staged<G, K, true>(pb, plan, tmap, value, loc, attn, out, out_bf16, st)  \
-                          : launch_staged<G, K, false>(pb, plan, tmap, value, loc, attn, out, out_bf16, st);
+        return value_bf16 ? launch_staged<G, K, true>(pb, plan, small, tmap, value, loc, attn, out, out_bf16, st)  \
+                          : launch_staged<G, K, false>(pb, plan, small, tmap, value, loc, attn, out, out_bf16, st);
     switch (nv) {
         MSDA_STAGED_CASE(2, 2, 1)
         MSDA_STAGED_CASE(4, 4, 1)

@@ -17,9 +17,9 @@ cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, 
                          const float* attn, void* out, bool out_bf16, cudaStream_t st);
 
 // msda_fwd_staged.cu
-bool forward_staged_supported(const Problem& pb, bool value_bf16);
+bool forward_staged_supported(const Problem& pb, bool value_bf16, bool small);
 cudaError_t forward_staged(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                           const float* attn, void* out, bool out_bf16, cudaStream_t st);
+                           const float* attn, void* out, bool out_bf16, bool small, cudaStream_t st);
 
 // msda_bwd.cu
 cudaError_t backward_flat(const Problem& pb, const void* value, bool value_bf16, const float* loc,
