@@ -52,7 +52,7 @@ struct SmemLayout {
     int off_g, off_rec, off_dots, off_bins, off_scan, off_order, total;
     __host__ __device__ SmemLayout(int qc, int P, int row_bytes, int bins_words) {
         off_g = 0;
-        off_rec = align16(qc * row_bytes);
+        off_rec = align16((qc + 1) * row_bytes);      // + one all-zero row read by idle visit slots
         off_dots = off_rec + qc * P * 16;
         off_bins = off_dots + qc * P * 16;
         off_scan = off_bins + align16(bins_words * 4);
@@ -244,6 +244,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         {
             for (int i = tid; i < nwords; i += THREADS) bins[i] = 0u;
             if (tid == 0) work_s[0] = 0;
+            if (tid < VPR) reinterpret_cast<uint4*>(smem + lay.off_g)[qc * VPR + tid] = make_uint4(0, 0, 0, 0);
             stage_samples();
             cp_async_commit();                               // group A: locations + attention
             const char* gsrc = grad_out + (((int64_t)n * pb.Lq + q0) * pb.H * pb.Dh + (int64_t)h * pb.Dh) * ES;
@@ -427,7 +428,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     for (int t = 0; t < trips; t += 4, j += 4 * split) {
                         const int jm = j + lane * split;
                         float w_m = 0.0f;
-                        uint32_t ga_m = 0xffffffffu, slot_m = 0u;
+                        uint32_t ga_m = a_g0 + qc * (VPR * 16), slot_m = 0u;      // idle slot: zero row, zero weight
                         if (jm < total) {
                             const bool up = jm < n_up;
                             const int e = jm + (up ? e0_up : delta_dn);
@@ -441,10 +442,10 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                         float d[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float w = __shfl_sync(FULL, w_m, u, 4);
-                            const uint32_t ga = __shfl_sync(FULL, ga_m, u, 4);
                             d[u] = 0.0f;
-                            if (ga != 0xffffffffu) {
+                            if (t + u < trips) {                              // warp-uniform
+                                const float w = __shfl_sync(FULL, w_m, u, 4);
+                                const uint32_t ga = __shfl_sync(FULL, ga_m, u, 4);
                                 float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll
                                 for (int k = 0; k < K; ++k) {
@@ -711,7 +712,7 @@ static bool make_plan(const Problem& pb, int row_bytes, GatherPlan& plan) {
     int max_bins = 0;
     for (int l = 0; l < pb.L; ++l) max_bins = max(max_bins, (pb.geom.w[l] + 1) * (pb.geom.h[l] + 1));
     plan.bins_words = (max_bins + 3) / 2;
-    const int fixed = align16(plan.bins_words * 4) + 64 * 4 + 32 * 64 * 2 + 16;
+    const int fixed = align16(plan.bins_words * 4) + 64 * 4 + 32 * 64 * 2 + 16 + row_bytes + 16;
     const int per_query = row_bytes + pb.P * 32;
     int qmax = (kMaxSmem - fixed) / per_query;
     qmax = min(qmax, min(65535 / pb.P, 4095));       // u16 counters / sample slots, 12-bit query ids

@@ -145,8 +145,11 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
         e = msda::forward_staged(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, small,
                                  (cudaStream_t)stream);
     } else {
+        // variants 4 / 5: the lean kernel compiled for 5 / 6 resident CTAs per SM (48 / 39 registers)
+        const int min_blocks = variant == 4 ? 5 : variant == 5 ? 6 : 4;
         e = (can_lean && variant != 0)
-            ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream)
+            ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, min_blocks,
+                                 (cudaStream_t)stream)
             : msda::forward_flat(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
     }
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward launch");

@@ -117,8 +117,8 @@ struct __align__(16) SampleParams {
     uint32_t off[4];     // byte offset of the corner row from the (n, h) base; ~0u: dropped corner
 };
 
-template <int G, int K, bool VBF, bool OBF>
-__global__ void __launch_bounds__(kFwdThreads, 4)
+template <int G, int K, bool VBF, bool OBF, int MINB>
+__global__ void __launch_bounds__(kFwdThreads, MINB)
 fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 const float* __restrict__ loc, const float* __restrict__ attn,
                 char* __restrict__ out) {
@@ -254,7 +254,7 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
 
 template <int G, int K, bool VBF>
 static cudaError_t launch_lean(const Problem& pb, const void* value, const float* loc, const float* attn,
-                               void* out, bool out_bf16, cudaStream_t st) {
+                               void* out, bool out_bf16, int min_blocks, cudaStream_t st) {
     constexpr int IPC = kFwdThreads / G;
     const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
     const unsigned grid = (unsigned)((items + IPC - 1) / IPC);
@@ -267,7 +267,12 @@ static cudaError_t launch_lean(const Problem& pb, const void* value, const float
         kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out);
         return cudaGetLastError();
     };
-    return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true>) : launch(fwd_lean_kernel<G, K, VBF, false>);
+    // min_blocks: occupancy target (registers per thread are capped accordingly); K == 1 only
+    if (K == 1 && min_blocks == 6)
+        return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 6>) : launch(fwd_lean_kernel<G, K, VBF, false, 6>);
+    if (K == 1 && min_blocks == 5)
+        return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 5>) : launch(fwd_lean_kernel<G, K, VBF, false, 5>);
+    return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 4>) : launch(fwd_lean_kernel<G, K, VBF, false, 4>);
 }
 
 // The lean kernel needs 32-bit row offsets and its parameter table in shared memory.
@@ -281,12 +286,12 @@ bool forward_lean_supported(const Problem& pb, bool value_bf16) {
 }
 
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, cudaStream_t st) {
+                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st) {
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
 #define MSDA_LEAN_CASE(NV, G, K)                                                          \
     case NV:                                                                              \
-        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, st)  \
-                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, st);
+        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, min_blocks, st)  \
+                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, min_blocks, st);
     switch (nv) {
         MSDA_LEAN_CASE(1, 1, 1)
         MSDA_LEAN_CASE(2, 2, 1)

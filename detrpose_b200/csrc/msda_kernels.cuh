@@ -14,7 +14,7 @@ cudaError_t forward_flat(const Problem& pb, const void* value, bool value_bf16, 
 
 bool forward_lean_supported(const Problem& pb, bool value_bf16);
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, cudaStream_t st);
+                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st);
 
 // msda_fwd_staged.cu
 bool forward_staged_supported(const Problem& pb, bool value_bf16, bool small);
