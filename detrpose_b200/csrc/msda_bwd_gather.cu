@@ -375,7 +375,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
             const bool rmw = accumulate || chunk > 0;
             // dense coarse levels: `split` groups share one pixel and take every split-th record
             int split = 1, split_log2 = 0;
-            while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 16 * npix * split)) {
+            while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 32 * npix * split)) {
                 split <<= 1;
                 ++split_log2;
             }
@@ -648,7 +648,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 *reinterpret_cast<float4*>(dots_s + slot * 4) = make_float4(ga, a * fW * gx, a * fH * gy, 0.0f);
             }
             __syncthreads();
-            MSDA_STAMP(7);
+            if (pbuf != nullptr && tid == 0 && chunk == 0) pbuf[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)l;
             if ((P & 3) == 0) {
                 const int vq = P / 4;
                 for (int i = tid; i < qc * vq; i += THREADS) {

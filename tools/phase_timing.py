@@ -33,11 +33,11 @@ def main():
     d = t[:, 1:7] - t[:, 0:6]
     names = ["P0 stage g", "P1 count", "P2 scan", "P3 scatter", "P4 pixels", "P5 samples"]
     out = {}
+    level = buf[:, 7].cpu()                       # the kernel records each CTA's level in slot 7
     for l in range(L):
-        sel = d[l::L]
-        out[f"level{l}"] = {n: round(float(sel[:, i].mean()), 0) for i, n in enumerate(names)}
-        out[f"level{l}"]["total"] = round(float((t[l::L, 6] - t[l::L, 0]).mean()), 0)
-        out[f"level{l}"]["P5a record sweep"] = round(float((t[l::L, 7] - t[l::L, 5]).mean()), 0)
+        m = level == l
+        out[f"level{l}"] = {n: round(float(d[m][:, i].mean()), 0) for i, n in enumerate(names)}
+        out[f"level{l}"]["total"] = round(float((t[m][:, 6] - t[m][:, 0]).mean()), 0)
     print(json.dumps(out, indent=1))
 
 
