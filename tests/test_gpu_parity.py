@@ -181,6 +181,38 @@ def test_model_shapes_vs_reference_ops_on_device(wl, N, Lq, degenerate, bwd_vari
     assert rel_err(got_g[2].cpu().numpy(), ref_g[2].cpu().numpy()) <= TOL
 
 
+def test_random_shapes_against_reference_ops_on_device(bwd_variant):
+    """Seeded sweep over odd shapes (tiny / non-square levels, 1..8 points, 1..4 levels, head dims 8..64,
+    query counts that are not multiples of anything): every kernel variant against the reference's op
+    sequence on the same device."""
+    rng = np.random.default_rng(1234)
+    for trial in range(24):
+        N = int(rng.integers(1, 4)); H = int(rng.choice([1, 2, 4, 8])); Dh = int(rng.choice([8, 16, 24, 32, 48, 64]))
+        L = int(rng.integers(1, 5)); P = int(rng.choice([1, 2, 3, 4, 6, 8])); Lq = int(rng.choice([1, 7, 33, 100, 257]))
+        shapes = tuple((int(rng.integers(1, 25)), int(rng.integers(1, 25))) for _ in range(L))
+        inp = synthetic.make_inputs(N, Lq, H, Dh, shapes, P, seed=100 + trial, device=DEV, clip=(-0.3, 1.3))
+        mem = inp["memory"].requires_grad_(True)
+        loc = inp["locations"].requires_grad_(True)
+        att = inp["attention"].requires_grad_(True)
+        ref_out = otorch.core(otorch.make_value_list(mem, H, shapes), shapes, loc, att)
+        ref_g = torch.autograd.grad(ref_out, [mem, loc, att], inp["grad_out"])
+        try:
+            out = dp.ms_deform_attn_core(otorch.make_value_list(mem, H, shapes), shapes, loc, att)
+            got_g = torch.autograd.grad(out, [mem, loc, att], inp["grad_out"])
+        except _lib.MSDAError as exc:
+            if "does not support this shape" in str(exc):
+                continue                                  # a forced variant refuses this shape (loudly)
+            raise
+        ia, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_UNFUSED)
+        ib, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_FMA)
+        keep = (ia == ib).all(-1, keepdim=True).float()
+        tag = f"trial {trial}: N={N} H={H} Dh={Dh} L={L} P={P} Lq={Lq} shapes={shapes}"
+        assert rel_err(out.detach().cpu().numpy(), ref_out.detach().cpu().numpy()) <= TOL, tag
+        assert rel_err(got_g[0].cpu().numpy(), ref_g[0].cpu().numpy()) <= TOL, tag
+        assert rel_err((got_g[1] * keep).cpu().numpy(), (ref_g[1] * keep).cpu().numpy()) <= TOL, tag
+        assert rel_err(got_g[2].cpu().numpy(), ref_g[2].cpu().numpy()) <= TOL, tag
+
+
 def test_full_size_properties():
     """BASELINE size (DETRPose-S, batch 64): properties that need no oracle.
 
