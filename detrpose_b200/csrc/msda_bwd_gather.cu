@@ -764,7 +764,7 @@ cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf1
         MSDA_GATHER_CASE(3, 1, 3, 512)
         MSDA_GATHER_CASE(4, 4, 1, 1024)
         MSDA_GATHER_CASE(6, 2, 3, 512)
-        MSDA_GATHER_CASE(8, 8, 1, 1024)
+        MSDA_GATHER_CASE(8, 4, 2, 1024)
         MSDA_GATHER_CASE(12, 4, 3, 512)
         MSDA_GATHER_CASE(16, 8, 2, 512)
         default: return cudaErrorInvalidValue;
