@@ -124,7 +124,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int PENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(PENDING) : "memory"); }
 
-template <int G, int K, bool VBF, int THREADS, bool SMALL>
+// ONE: the whole query range fits one chunk and grad_value is overwritten -- the common case; the
+// read-modify-write paths and the chunk bookkeeping compile away (less register pressure).
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float* __restrict__ loc,
                   const float* __restrict__ attn, const char* __restrict__ grad_out,
@@ -372,7 +374,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
 
         // ---- P4: pixel owners gather ----
         {
-            const bool rmw = accumulate || chunk > 0;
+            const bool rmw = !ONE && (accumulate || chunk > 0);
             // dense coarse levels: `split` groups share one pixel and take every split-th record
             int split = 1, split_log2 = 0;
             while (split < UPW && (npix * split < (THREADS / G) * 2 || nsamp * 4 > 32 * npix * split)) {
@@ -679,11 +681,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
 #undef MSDA_STAMP
 }
 
-template <int G, int K, bool VBF, int THREADS, bool SMALL>
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE>
 static cudaError_t launch_gather_impl(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
                                       const float* attn, const void* go, float* gv, float* gl, float* ga,
                                       int accumulate, cudaStream_t st) {
-    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL>;
+    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL, ONE>;
     static thread_local int configured_for = -1;      // per-thread cache of the attribute call (per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -702,9 +704,11 @@ template <int G, int K, bool VBF, int THREADS>
 static cudaError_t launch_gather(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
                                  const float* attn, const void* go, float* gv, float* gl, float* ga,
                                  int accumulate, cudaStream_t st) {
-    return gl != nullptr
-        ? launch_gather_impl<G, K, VBF, THREADS, true>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st)
-        : launch_gather_impl<G, K, VBF, THREADS, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
+    const bool one = plan.n_chunks == 1 && !accumulate;
+    if (gl != nullptr)
+        return one ? launch_gather_impl<G, K, VBF, THREADS, true, true>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st)
+                   : launch_gather_impl<G, K, VBF, THREADS, true, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
+    return launch_gather_impl<G, K, VBF, THREADS, false, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
 }
 
 // Returns false when the shape does not fit the gather kernel (caller falls back to the flat one).
