@@ -737,10 +737,16 @@ bool backward_gather_supported(const Problem& pb, bool value_bf16) {
 
 cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                             const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
-                            float* grad_attn, int accumulate, bool wide_regs, cudaStream_t st) {
+                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st) {
     GatherPlan plan;
     if (!make_plan(pb, pb.Dh * (value_bf16 ? 2 : 4), plan)) return cudaErrorInvalidValue;
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
+    const bool wide_regs = threads_pref == 512;
+    if (threads_pref == 768 && nv == 4)          // 768 threads x 85 registers
+        return value_bf16 ? launch_gather<4, 1, true, 768>(pb, plan, value, loc, attn, grad_out, grad_value,
+                                                           grad_loc, grad_attn, accumulate, st)
+                          : launch_gather<4, 1, false, 768>(pb, plan, value, loc, attn, grad_out, grad_value,
+                                                            grad_loc, grad_attn, accumulate, st);
     if (wide_regs) {          // 512 threads x 128 registers instead of 1024 x 64
 #define MSDA_GATHER_WIDE(NV, G, K)                                                                          \
     case NV:                                                                                                \

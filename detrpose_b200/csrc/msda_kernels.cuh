@@ -30,7 +30,7 @@ cudaError_t backward_flat(const Problem& pb, const void* value, bool value_bf16,
 bool backward_gather_supported(const Problem& pb, bool value_bf16);
 cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                             const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
-                            float* grad_attn, int accumulate, bool wide_regs, cudaStream_t st);
+                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st);
 
 cudaError_t set_phase_buffer(unsigned long long* buf);
 
