@@ -359,9 +359,58 @@ def sample_indices(sampling_locations: torch.Tensor, spatial_shapes, coord_mode:
     return idx, starts
 
 
+class _Prologue(torch.autograd.Function):
+    """Fused softmax + location kernel with an analytic backward (elementwise torch ops)."""
+
+    @staticmethod
+    def forward(ctx, offsets, logits, ref_points, meta):
+        shapes, n_heads, n_levels, n_points = meta
+        loc, att = _locations_raw(offsets, logits, ref_points, shapes, n_heads, n_levels, n_points)
+        ctx.meta = meta
+        ctx.shapes_in = (offsets.shape, logits.shape, ref_points.shape)
+        ctx.save_for_backward(att)
+        return loc, att
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_loc, grad_att):
+        shapes, n_heads, n_levels, n_points = ctx.meta
+        (att,) = ctx.saved_tensors
+        off_shape, lg_shape, ref_shape = ctx.shapes_in
+        n, lq = att.shape[:2]
+        g_off = g_lg = g_ref = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            grad_loc = grad_loc.float()
+            if ctx.needs_input_grad[0]:
+                norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32, device=att.device)
+                g_off = (grad_loc / norm.view(1, 1, 1, n_levels, 1, 2)).reshape(off_shape)
+            if ctx.needs_input_grad[2]:
+                g_ref = grad_loc.sum(dim=(2, 4))                       # over heads and points -> (N, Lq, L, 2)
+                if ref_shape[2] == 1:
+                    g_ref = g_ref.sum(dim=2, keepdim=True)
+                g_ref = g_ref.reshape(ref_shape)
+        if ctx.needs_input_grad[1]:
+            a = att.view(n, lq, n_heads, n_levels * n_points)
+            g = grad_att.float().reshape(n, lq, n_heads, n_levels * n_points)
+            g_lg = (a * (g - (a * g).sum(-1, keepdim=True))).reshape(lg_shape)
+        return g_off, g_lg, g_ref, None
+
+
 def locations_and_weights(offsets: torch.Tensor, logits: torch.Tensor, ref_points: torch.Tensor,
                           spatial_shapes, n_heads: int, n_levels: int, n_points: int):
-    """Fused prologue (no autograd): softmax over L*P and ``ref + offsets / (W_l, H_l)``.
+    """Fused prologue, differentiable: softmax over L*P and ``ref + offsets / (W_l, H_l)``.
+
+    ms_deform_attn.py:392-393 and :412-416.  ``offsets`` ``(N, Lq, H*L*P*2)``, ``logits``
+    ``(N, Lq, H*L*P)``, ``ref_points`` ``(N, Lq, 1|L, 2)``, all fp32.  Returns fp32
+    ``(locations (N, Lq, H, L, P, 2), attention (N, Lq, H, L, P))``.
+    """
+    shapes = _shapes_tuple(spatial_shapes)
+    return _Prologue.apply(offsets, logits, ref_points, (shapes, n_heads, n_levels, n_points))
+
+
+def _locations_raw(offsets: torch.Tensor, logits: torch.Tensor, ref_points: torch.Tensor,
+                   spatial_shapes, n_heads: int, n_levels: int, n_points: int):
+    """Fused prologue launch (no autograd): softmax over L*P and ``ref + offsets / (W_l, H_l)``.
 
     ms_deform_attn.py:392-393 and :412-416.  ``offsets`` ``(N, Lq, H*L*P*2)``, ``logits``
     ``(N, Lq, H*L*P)``, ``ref_points`` ``(N, Lq, 1|L, 2)``.  Returns fp32

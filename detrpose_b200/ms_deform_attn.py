@@ -59,7 +59,7 @@ class MSDeformAttn(nn.Module):
         self.num_groups = 1
         self.use_4D_normalizer = use_4D_normalizer
         self.region_kernel_size = int(region_kernel_size)
-        self.fuse_prologue = True          # fused softmax/location kernel when no autograd graph is needed
+        self.fuse_prologue = True          # fused softmax/location kernel (fp32 inputs, 2-D reference points)
 
         self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
         self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
@@ -101,10 +101,8 @@ class MSDeformAttn(nn.Module):
         if last not in (2, 4):
             raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(last))
 
-        needs_graph = torch.is_grad_enabled() and (
-            offsets.requires_grad or logits.requires_grad or ref.requires_grad)
         all_f32 = offsets.dtype == logits.dtype == ref.dtype == torch.float32
-        if last == 2 and self.fuse_prologue and not needs_graph and all_f32:
+        if last == 2 and self.fuse_prologue and all_f32 and offsets.is_cuda:
             locations, weights = MF.locations_and_weights(offsets, logits, ref, shapes, H, L, P)
         else:
             offsets = offsets.view(N, Len_q, H, L, P, 2)

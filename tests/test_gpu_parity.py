@@ -349,6 +349,17 @@ def test_fused_prologue_locations_bit_exact():
     att_ref = torch.softmax(logits.view(3, 50, H, L * P), -1).view(3, 50, H, L, P)
     assert torch.equal(loc, loc_ref)
     assert rel_err(att.cpu().numpy(), att_ref.cpu().numpy()) <= 1e-6
+    # analytic backward of the fused prologue against autograd through the reference's torch ops
+    o1, l1, r1 = (t.clone().requires_grad_(True) for t in (offsets, logits, ref))
+    o2, l2, r2 = (t.clone().requires_grad_(True) for t in (offsets, logits, ref))
+    gl, ga = torch.randn_like(loc), torch.randn_like(att)
+    loc1, att1 = dp.locations_and_weights(o1, l1, r1, shapes, H, L, P)
+    g1 = torch.autograd.grad([loc1, att1], [o1, l1, r1], [gl, ga])
+    loc2 = r2[:, :, None, :, None, :] + o2.view(3, 50, H, L, P, 2) / norm
+    att2 = torch.softmax(l2.view(3, 50, H, L * P), -1).view(3, 50, H, L, P)
+    g2 = torch.autograd.grad([loc2, att2], [o2, l2, r2], [gl, ga])
+    for a, b in zip(g1, g2):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
 
 
 def test_backward_from_worker_thread_and_non_default_stream():
