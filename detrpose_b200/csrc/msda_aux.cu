@@ -150,6 +150,137 @@ unpack_grad_kernel(const Problem pb, const float* __restrict__ gv, const LevelVi
     }
 }
 
+// ---------------------------------------------------------------------------
+// Vectorised repack / un-repack for the layout the reference actually hands over for N > 1
+// (spatial stride 1, 16-byte aligned rows): 64 positions x Dh channels per block, 16-byte global
+// accesses on both sides, fp32 staging tile in shared memory with a 65-word pitch (conflict-free
+// on the transposed side).  Anything else takes the scalar kernels above.
+// ---------------------------------------------------------------------------
+constexpr int kVecTileS = 64;
+
+struct TileMap64 { int32_t first_tile[MSDA_MAX_LEVELS + 1]; };
+
+template <bool BF> struct ElemVec { static constexpr int n = BF ? 8 : 4; };
+
+template <bool BF>
+__device__ __forceinline__ void vec_to_floats(const uint4& v, float* f) {
+    if constexpr (BF) {
+        f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+        f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+    } else {
+        f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y); f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+    }
+}
+template <bool BF>
+__device__ __forceinline__ uint4 floats_to_vec(const float* f) {
+    if constexpr (BF)
+        return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    else
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+}
+
+template <bool SBF, bool DBF>
+__global__ void __launch_bounds__(256)
+repack_vec_kernel(const Problem pb, const LevelViews src, const TileMap64 tm, char* __restrict__ dst) {
+    extern __shared__ float tile[];                   // [Dh][65]
+    constexpr int VS = ElemVec<SBF>::n, VD = ElemVec<DBF>::n, PITCH = kVecTileS + 1;
+    const int nh = blockIdx.y, n = nh / pb.H, h = nh % pb.H;
+    int l = 0;
+    while (l + 1 < pb.L && (int)blockIdx.x >= tm.first_tile[l + 1]) ++l;
+    const int s0 = ((int)blockIdx.x - tm.first_tile[l]) * kVecTileS;
+    const int hw = pb.geom.h[l] * pb.geom.w[l];
+    const char* sp = reinterpret_cast<const char*>(src.ptr[l]);
+    constexpr int SES = SBF ? 2 : 4, DES = DBF ? 2 : 4;
+    // load: channel rows, VS positions per 16-byte vector
+    for (int idx = threadIdx.x; idx < pb.Dh * (kVecTileS / VS); idx += 256) {
+        const int c = idx / (kVecTileS / VS), v = idx % (kVecTileS / VS);
+        const int s = s0 + v * VS;
+        float f[VS];
+        const int64_t e = (int64_t)nh * src.s_nh[l] + (int64_t)c * src.s_c[l] + s;
+        if (s + VS <= hw) {
+            vec_to_floats<SBF>(__ldg(reinterpret_cast<const uint4*>(sp + e * SES)), f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VS; ++j) f[j] = (s + j < hw) ? load_elem<SBF>(sp, e + j) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < VS; ++j) tile[c * PITCH + v * VS + j] = f[j];
+    }
+    __syncthreads();
+    // store: position rows, VD channels per 16-byte vector
+    const int64_t drow = (int64_t)pb.H * pb.Dh;
+    for (int idx = threadIdx.x; idx < kVecTileS * (pb.Dh / VD); idx += 256) {
+        const int p = idx / (pb.Dh / VD), cv = idx % (pb.Dh / VD);
+        if (s0 + p >= hw) continue;
+        float f[VD];
+#pragma unroll
+        for (int j = 0; j < VD; ++j) f[j] = tile[(cv * VD + j) * PITCH + p];
+        const int64_t d = ((int64_t)n * pb.S + pb.geom.start[l] + s0 + p) * drow + (int64_t)h * pb.Dh + cv * VD;
+        *reinterpret_cast<uint4*>(dst + d * DES) = floats_to_vec<DBF>(f);
+    }
+}
+
+template <bool DBF>
+__global__ void __launch_bounds__(256)
+unpack_grad_vec_kernel(const Problem pb, const float* __restrict__ gv, const LevelViews dst, const TileMap64 tm) {
+    extern __shared__ float tile[];                   // [Dh][65]
+    constexpr int VD = ElemVec<DBF>::n, PITCH = kVecTileS + 1, DES = DBF ? 2 : 4;
+    const int nh = blockIdx.y, n = nh / pb.H, h = nh % pb.H;
+    int l = 0;
+    while (l + 1 < pb.L && (int)blockIdx.x >= tm.first_tile[l + 1]) ++l;
+    const int s0 = ((int)blockIdx.x - tm.first_tile[l]) * kVecTileS;
+    const int hw = pb.geom.h[l] * pb.geom.w[l];
+    const int64_t srow = (int64_t)pb.H * pb.Dh;
+    for (int idx = threadIdx.x; idx < kVecTileS * (pb.Dh / 4); idx += 256) {
+        const int p = idx / (pb.Dh / 4), cv = idx % (pb.Dh / 4);
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s0 + p < hw)
+            f = __ldg(reinterpret_cast<const float4*>(
+                gv + ((int64_t)n * pb.S + pb.geom.start[l] + s0 + p) * srow + (int64_t)h * pb.Dh + cv * 4));
+        tile[(cv * 4 + 0) * PITCH + p] = f.x; tile[(cv * 4 + 1) * PITCH + p] = f.y;
+        tile[(cv * 4 + 2) * PITCH + p] = f.z; tile[(cv * 4 + 3) * PITCH + p] = f.w;
+    }
+    __syncthreads();
+    char* dp = reinterpret_cast<char*>(const_cast<void*>(dst.ptr[l]));
+    for (int idx = threadIdx.x; idx < pb.Dh * (kVecTileS / VD); idx += 256) {
+        const int c = idx / (kVecTileS / VD), v = idx % (kVecTileS / VD);
+        const int s = s0 + v * VD;
+        if (s >= hw) continue;
+        float f[VD];
+#pragma unroll
+        for (int j = 0; j < VD; ++j) f[j] = tile[c * PITCH + v * VD + j];
+        const int64_t e = (int64_t)nh * dst.s_nh[l] + (int64_t)c * dst.s_c[l] + s;
+        if (s + VD <= hw) {
+            *reinterpret_cast<uint4*>(dp + e * DES) = floats_to_vec<DBF>(f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VD; ++j) if (s + j < hw) store_elem<DBF>(dp, e + j, f[j]);
+        }
+    }
+}
+
+// the vector kernels need unit spatial stride and 16-byte aligned channel rows on the strided side
+static bool views_vectorisable(const Problem& pb, const LevelViews& v, bool bf16) {
+    const int es = bf16 ? 2 : 4;
+    if (pb.Dh % 8 != 0) return false;
+    for (int l = 0; l < pb.L; ++l) {
+        if (v.s_s[l] != 1) return false;
+        if ((reinterpret_cast<uintptr_t>(v.ptr[l]) & 15u) || (v.s_nh[l] * es) % 16 || (v.s_c[l] * es) % 16) return false;
+    }
+    return true;
+}
+
+static TileMap64 make_tile_map64(const Problem& pb) {
+    TileMap64 tm;
+    int acc = 0;
+    for (int l = 0; l < pb.L; ++l) {
+        tm.first_tile[l] = acc;
+        acc += (pb.geom.h[l] * pb.geom.w[l] + kVecTileS - 1) / kVecTileS;
+    }
+    for (int l = pb.L; l <= MSDA_MAX_LEVELS; ++l) tm.first_tile[l] = acc;
+    return tm;
+}
+
 static TileMap make_tile_map(const Problem& pb) {
     TileMap tm;
     int acc = 0;
@@ -163,6 +294,19 @@ static TileMap make_tile_map(const Problem& pb) {
 
 cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void* dst, bool dst_bf16,
                    cudaStream_t st) {
+    if (views_vectorisable(pb, src, src_bf16) && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const TileMap64 tm64 = make_tile_map64(pb);
+        const dim3 grid(tm64.first_tile[pb.L], pb.N * pb.H);
+        const size_t smem = (size_t)pb.Dh * (kVecTileS + 1) * sizeof(float);
+        if (src_bf16) {
+            if (dst_bf16) repack_vec_kernel<true, true><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
+            else repack_vec_kernel<true, false><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
+        } else {
+            if (dst_bf16) repack_vec_kernel<false, true><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
+            else repack_vec_kernel<false, false><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
+        }
+        return cudaGetLastError();
+    }
     const TileMap tm = make_tile_map(pb);
     const dim3 grid(tm.first_tile[pb.L], pb.N * pb.H);
     const size_t smem = (size_t)pb.Dh * (kTileS + 1) * sizeof(float);
@@ -178,6 +322,14 @@ cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void
 
 cudaError_t unpack_grad(const Problem& pb, const float* grad_value, const LevelViews& dst, bool dst_bf16,
                         cudaStream_t st) {
+    if (views_vectorisable(pb, dst, dst_bf16) && (reinterpret_cast<uintptr_t>(grad_value) & 15u) == 0) {
+        const TileMap64 tm64 = make_tile_map64(pb);
+        const dim3 grid(tm64.first_tile[pb.L], pb.N * pb.H);
+        const size_t smem = (size_t)pb.Dh * (kVecTileS + 1) * sizeof(float);
+        if (dst_bf16) unpack_grad_vec_kernel<true><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);
+        else unpack_grad_vec_kernel<false><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);
+        return cudaGetLastError();
+    }
     const TileMap tm = make_tile_map(pb);
     const dim3 grid(tm.first_tile[pb.L], pb.N * pb.H);
     const size_t smem = (size_t)pb.Dh * (kTileS + 1) * sizeof(float);
