@@ -9,9 +9,10 @@ and function interface.  See DESIGN.md and INTEGRATION.md.
 from .functional import (ms_deform_attn_core, sample_indices, level_start_index, locations_and_weights,
                          pack_value, clear_repack_cache, set_default_coord_mode, get_default_coord_mode)
 from .ms_deform_attn import MSDeformAttn
+from .gate import Gate, gate_epilogue
 from . import patch, synthetic, shard
 
-__all__ = ["MSDeformAttn", "ms_deform_attn_core", "sample_indices", "level_start_index",
+__all__ = ["MSDeformAttn", "Gate", "gate_epilogue", "ms_deform_attn_core", "sample_indices", "level_start_index",
            "locations_and_weights", "pack_value", "clear_repack_cache", "set_default_coord_mode",
            "get_default_coord_mode", "patch", "synthetic", "shard"]
 __version__ = "0.1.0"

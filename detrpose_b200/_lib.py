@@ -10,7 +10,7 @@ import ctypes
 import os
 import subprocess
 import threading
-from ctypes import c_char_p, c_int, c_int32, c_int64, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsda_b200.so")
@@ -43,6 +43,11 @@ SIGNATURES = {
                                  c_int, c_int, c_int, c_int, c_void_p]),
     "msda_b200_unpack_grad": (c_int, [c_void_p, _I32P, _VPP, _I64P, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p]),
+    "msda_b200_gate_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
+                                       c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "msda_b200_gate_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                        c_void_p]),
 }
 
 _lock = threading.Lock()

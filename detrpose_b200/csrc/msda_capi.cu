@@ -253,4 +253,49 @@ MSDA_API int msda_b200_unpack_grad(const float* grad_value, const int32_t* spati
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_unpack_grad launch");
 }
 
+namespace {
+int check_gate(const void* pre, int pre_dtype, const void* x1, const void* x2, int x_dtype, int64_t rows, int C) {
+    if (pre == nullptr || x1 == nullptr || x2 == nullptr) return fail(MSDA_ERR_NULL, "gate: NULL input");
+    if ((pre_dtype != MSDA_F32 && pre_dtype != MSDA_BF16) || (x_dtype != MSDA_F32 && x_dtype != MSDA_BF16))
+        return fail(MSDA_ERR_DTYPE, "gate: unknown dtype %d / %d", pre_dtype, x_dtype);
+    if (rows <= 0) return fail(MSDA_ERR_SHAPE, "gate: rows=%lld", (long long)rows);
+    if (!msda::gate_supported(C)) return fail(MSDA_ERR_SHAPE, "gate: C=%d unsupported (128, 256, 384, 512)", C);
+    if (!aligned16(pre) || !aligned16(x1) || !aligned16(x2)) return fail(MSDA_ERR_ALIGN, "gate: unaligned input");
+    return MSDA_OK;
+}
+}  // namespace
+
+MSDA_API int msda_b200_gate_forward(const void* pre, int pre_dtype, const void* x1, const void* x2, int x_dtype,
+                                    const float* gamma, const float* beta, float eps, void* y, float* stats,
+                                    int64_t rows, int C, void* stream) {
+    if (int rc = check_gate(pre, pre_dtype, x1, x2, x_dtype, rows, C)) return rc;
+    if (gamma == nullptr || beta == nullptr || y == nullptr) return fail(MSDA_ERR_NULL, "gate: NULL gamma/beta/y");
+    if (!aligned16(gamma) || !aligned16(beta) || !aligned16(y) || (reinterpret_cast<uintptr_t>(stats) & 7u))
+        return fail(MSDA_ERR_ALIGN, "gate: unaligned gamma/beta/y/stats");
+    const cudaError_t e = msda::gate_forward(pre, pre_dtype == MSDA_BF16, x1, x2, x_dtype == MSDA_BF16, gamma, beta,
+                                             eps, y, stats, rows, C, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "gate forward launch");
+}
+
+MSDA_API int msda_b200_gate_backward(const void* pre, int pre_dtype, const void* x1, const void* x2, int x_dtype,
+                                     const float* gamma, const float* stats, const void* grad_y, void* grad_pre,
+                                     void* grad_x1, void* grad_x2, float* grad_gamma, float* grad_beta,
+                                     int64_t rows, int C, void* stream) {
+    if (int rc = check_gate(pre, pre_dtype, x1, x2, x_dtype, rows, C)) return rc;
+    if (gamma == nullptr || stats == nullptr || grad_y == nullptr || grad_pre == nullptr || grad_x1 == nullptr ||
+        grad_x2 == nullptr || grad_gamma == nullptr || grad_beta == nullptr)
+        return fail(MSDA_ERR_NULL, "gate backward: NULL argument");
+    if (!aligned16(gamma) || !aligned16(grad_y) || !aligned16(grad_pre) || !aligned16(grad_x1) ||
+        !aligned16(grad_x2) || (reinterpret_cast<uintptr_t>(stats) & 7u))
+        return fail(MSDA_ERR_ALIGN, "gate backward: unaligned argument");
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "gate backward: device query");
+    e = msda::gate_backward(pre, pre_dtype == MSDA_BF16, x1, x2, x_dtype == MSDA_BF16, gamma, stats, grad_y,
+                            grad_pre, grad_x1, grad_x2, grad_gamma, grad_beta, rows, C, sms, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "gate backward launch");
+}
+
+
 }  // extern "C"

@@ -48,4 +48,13 @@ cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void
 cudaError_t unpack_grad(const Problem& pb, const float* grad_value, const LevelViews& dst, bool dst_bf16,
                         cudaStream_t st);
 
+// msda_gate.cu
+bool gate_supported(int C);
+cudaError_t gate_forward(const void* pre, bool pre_bf16, const void* x1, const void* x2, bool x_bf16,
+                         const float* gamma, const float* beta, float eps, void* y, float* stats, int64_t rows,
+                         int C, cudaStream_t st);
+cudaError_t gate_backward(const void* pre, bool pre_bf16, const void* x1, const void* x2, bool x_bf16,
+                          const float* gamma, const float* stats, const void* gy, void* gpre, void* gx1, void* gx2,
+                          float* ggamma, float* gbeta, int64_t rows, int C, int sm_count, cudaStream_t st);
+
 }  // namespace msda

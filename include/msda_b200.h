@@ -177,6 +177,33 @@ MSDA_API int msda_b200_unpack_grad(const float* grad_value, const int32_t* spati
                           void* const* level_ptrs, const int64_t* level_strides, int dst_dtype,
                           int N, int H, int Dh, int L, void* stream);
 
+/*
+ * Gate epilogue -- replaces everything after the Linear in
+ * Gate.forward, transformer.py:233-235 (sigmoid, chunk, blend, LayerNorm with affine):
+ *   y = LayerNorm(sigmoid(pre[:, :C]) * x1 + sigmoid(pre[:, C:]) * x2) * gamma + beta
+ *
+ * pre     device (rows, 2*C) contiguous, pre_dtype: output of the 2C->2C Linear, BEFORE the sigmoid
+ * x1, x2  device (rows, C) contiguous, x_dtype (the layer input and the sampler output, :429)
+ * gamma, beta  device fp32 [C] (LayerNorm weight / bias); eps as in nn.LayerNorm
+ * y       device (rows, C) contiguous, x_dtype
+ * stats   device fp32 (rows, 2) receiving (mean, rstd) per row for the backward, or NULL (inference)
+ * C in {128, 256, 384, 512}; all pointers 16-byte aligned.
+ */
+MSDA_API int msda_b200_gate_forward(const void* pre, int pre_dtype, const void* x1, const void* x2, int x_dtype,
+                           const float* gamma, const float* beta, float eps,
+                           void* y, float* stats, int64_t rows, int C, void* stream);
+
+/*
+ * Backward of the gate epilogue (the reference gets it from autograd over the same ops).
+ * grad_y (rows, C) x_dtype;  outputs, all overwritten: grad_pre (rows, 2*C) pre_dtype,
+ * grad_x1 / grad_x2 (rows, C) x_dtype, grad_gamma / grad_beta fp32 [C] (zero-filled by the
+ * library, then summed over rows with fp32 atomics: summation order is not fixed).
+ */
+MSDA_API int msda_b200_gate_backward(const void* pre, int pre_dtype, const void* x1, const void* x2, int x_dtype,
+                            const float* gamma, const float* stats, const void* grad_y,
+                            void* grad_pre, void* grad_x1, void* grad_x2,
+                            float* grad_gamma, float* grad_beta, int64_t rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

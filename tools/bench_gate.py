@@ -1,0 +1,171 @@
+"""Gate epilogue on the DETRPose-S decoder shape: rows = batch x 1080 queries,
+C = 256.  Times the fused kernels against the same ops issued through PyTorch on this GPU (the
+reference's sequence, transformer.py:231-235) and reports algorithmic GB/s against the measured HBM peak.
+
+Algorithmic bytes per row (each operand once): forward  2C*e_p + 2C*e_x (in) + C*e_x (out) + 8 (mean, rstd);
+backward 2C*e_p + 3C*e_x + 8 (in) + 2C*e_p + 2C*e_x (out).
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from detrpose_b200.gate import Gate, gate_epilogue                  # noqa: E402
+from detrpose_b200 import _lib                                      # noqa: E402
+from detrpose_b200.functional import _code, _stream_ptr             # noqa: E402
+
+
+def _peak():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"])
+    except Exception:
+        return 6555.5
+
+
+def _time(fn, warmup=20, reps=100):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _time_stream(fn, warmup=20, reps=200):
+    """Back-to-back asynchronous launches between two events: device time per launch."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def reference_epilogue(pre, x1, x2, gamma, beta, eps):
+    gates = torch.sigmoid(pre)
+    g1, g2 = gates.chunk(2, dim=-1)
+    return F.layer_norm(g1 * x1 + g2 * x2, (x1.shape[-1],), gamma, beta, eps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--lq", type=int, default=1080)
+    ap.add_argument("--C", type=int, default=256)
+    args = ap.parse_args()
+    dev, peak = "cuda:0", _peak()
+    rows, C = args.batch * args.lq, args.C
+    out = {"rows": rows, "C": C, "peak_GBps": peak}
+    for name, dt in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        e = 2 if dt == torch.bfloat16 else 4
+        torch.manual_seed(0)
+        pre = torch.randn(rows, 2 * C, device=dev, dtype=dt, requires_grad=True)
+        x1 = torch.randn(rows, C, device=dev, dtype=dt, requires_grad=True)
+        x2 = torch.randn(rows, C, device=dev, dtype=dt, requires_grad=True)
+        # the kernel-only loop rotates over SETS copies of every operand: > 1 GB touched between two uses
+        # of the same buffer, so nothing is served from the 126 MB L2
+        SETS = 6
+        rot = [[torch.randn_like(t) for t in (pre, x1, x2)] + [torch.randn(rows, C, device=dev, dtype=dt)]
+               for _ in range(SETS)]
+        turn = [0, 0]
+        gamma = torch.ones(C, device=dev, requires_grad=True)
+        beta = torch.zeros(C, device=dev, requires_grad=True)
+        gy = torch.randn(rows, C, device=dev, dtype=dt)
+        b_f = rows * (2 * C * e + 2 * C * e + C * e + 8)
+        b_b = rows * (2 * C * e + 3 * C * e + 8 + 2 * C * e + 2 * C * e)
+        leaves = [pre, x1, x2, gamma, beta]
+
+        # the kernels alone, through the C ABI (no autograd / allocator time between launches)
+        lib = _lib.load()
+        y = torch.empty_like(x1)
+        st = torch.empty(rows, 2, device=dev)
+        gp, g1, g2 = torch.empty_like(pre), torch.empty_like(x1), torch.empty_like(x2)
+        ggb = torch.empty(2, C, device=dev)
+        sp = _stream_ptr(torch.device(dev))
+
+        def fwd_ours():
+            p_, a_, b_, _ = rot[turn[0] % SETS]
+            turn[0] += 1
+            _lib.check(lib.msda_b200_gate_forward(p_.data_ptr(), _code(dt), a_.data_ptr(), b_.data_ptr(), _code(dt),
+                                                  gamma.data_ptr(), beta.data_ptr(), 1e-5, y.data_ptr(),
+                                                  st.data_ptr(), rows, C, sp), "gate fwd")
+
+        def bwd_ours():
+            p_, a_, b_, g_ = rot[turn[1] % SETS]
+            turn[1] += 1
+            _lib.check(lib.msda_b200_gate_backward(p_.data_ptr(), _code(dt), a_.data_ptr(), b_.data_ptr(), _code(dt),
+                                                   gamma.data_ptr(), st.data_ptr(), g_.data_ptr(), gp.data_ptr(),
+                                                   g1.data_ptr(), g2.data_ptr(), ggb[0].data_ptr(),
+                                                   ggb[1].data_ptr(), rows, C, sp), "gate bwd")
+
+        def fwd_ref():
+            return reference_epilogue(pre, x1, x2, gamma.to(dt), beta.to(dt), 1e-5)
+
+        y_r = fwd_ref()
+        t_fo = _time_stream(fwd_ours)
+        t_bo = _time_stream(bwd_ours)
+        t_fr = _time_stream(fwd_ref, 10, 50)
+        t_br = _time_stream(lambda: torch.autograd.grad(y_r, leaves, gy, retain_graph=True), 10, 50)
+        gbs = (b_f + b_b) / ((t_fo + t_bo) * 1e-3) / 1e9
+        out[name] = {"fwd_ms": round(t_fo, 4), "bwd_ms": round(t_bo, 4),
+                     "fwd_GBps": round(b_f / t_fo / 1e6, 1), "bwd_GBps": round(b_b / t_bo / 1e6, 1),
+                     "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4),
+                     "torch_ops_fwd_ms": round(t_fr, 4), "torch_ops_bwd_ms": round(t_br, 4),
+                     "speedup_vs_torch_ops": round((t_fr + t_br) / (t_fo + t_bo), 2)}
+        del y_r, rot
+        torch.cuda.empty_cache()
+
+    # whole block (GEMM included), fp32 parameters under bf16 autocast as in training, and plain fp32
+    ours = Gate(C).to(dev)
+    with torch.no_grad():
+        ours.gate.weight.normal_(0, 0.03)
+
+    class RefGate(torch.nn.Module):                      # the reference's op sequence (transformer.py:231-235)
+        def __init__(self, src):
+            super().__init__()
+            self.gate, self.norm = src.gate, src.norm
+
+        def forward(self, a, b):
+            gates = torch.sigmoid(self.gate(torch.cat([a, b], dim=-1)))
+            g1, g2 = gates.chunk(2, dim=-1)
+            return self.norm(g1 * a + g2 * b)
+
+    ref = RefGate(ours)
+    x1 = torch.randn(args.batch, args.lq, C, device=dev, requires_grad=True)
+    x2 = torch.randn(args.batch, args.lq, C, device=dev, requires_grad=True)
+    gy = torch.randn(args.batch, args.lq, C, device=dev)
+
+    def step(m, autocast):
+        def run():
+            for p in list(m.parameters()) + [x1, x2]:
+                p.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                y = m(x1, x2)
+            y.backward(gy)
+        return run
+
+    for tag, ac in (("block_fp32", False), ("block_autocast_bf16", True)):
+        t_o, t_r = _time(step(ours, ac), 10, 50), _time(step(ref, ac), 10, 50)
+        out[tag] = {"ours_fwd_bwd_ms": round(t_o, 4), "reference_ops_fwd_bwd_ms": round(t_r, 4),
+                    "speedup": round(t_r / t_o, 2)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
