@@ -10,9 +10,10 @@ from .functional import (ms_deform_attn_core, sample_indices, level_start_index,
                          pack_value, clear_repack_cache, set_default_coord_mode, get_default_coord_mode)
 from .ms_deform_attn import MSDeformAttn
 from .gate import Gate, gate_epilogue
+from .lqe import LQE, lqe_statistics
 from . import patch, synthetic, shard
 
-__all__ = ["MSDeformAttn", "Gate", "gate_epilogue", "ms_deform_attn_core", "sample_indices", "level_start_index",
+__all__ = ["MSDeformAttn", "Gate", "gate_epilogue", "LQE", "lqe_statistics", "ms_deform_attn_core", "sample_indices", "level_start_index",
            "locations_and_weights", "pack_value", "clear_repack_cache", "set_default_coord_mode",
            "get_default_coord_mode", "patch", "synthetic", "shard"]
 __version__ = "0.1.0"

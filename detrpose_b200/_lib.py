@@ -48,6 +48,10 @@ SIGNATURES = {
     "msda_b200_gate_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                         c_void_p]),
+    "msda_b200_lqe_forward": (c_int, [c_void_p, c_int, _I64P, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msda_b200_lqe_backward": (c_int, [c_void_p, c_int, _I64P, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lock = threading.Lock()

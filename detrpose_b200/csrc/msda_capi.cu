@@ -298,4 +298,45 @@ MSDA_API int msda_b200_gate_backward(const void* pre, int pre_dtype, const void*
 }
 
 
+namespace {
+int check_lqe(const void* feat, int feat_dtype, const int64_t* strides, const float* poses, int B, int C, int Hf,
+              int Wf, int P, int K, int coord_mode) {
+    if (feat == nullptr || strides == nullptr || poses == nullptr) return fail(MSDA_ERR_NULL, "lqe: NULL input");
+    if (feat_dtype != MSDA_F32 && feat_dtype != MSDA_BF16) return fail(MSDA_ERR_DTYPE, "lqe: unknown dtype %d", feat_dtype);
+    if (B <= 0 || P <= 0 || Hf <= 0 || Wf <= 0 || Hf > 16384 || Wf > 16384)
+        return fail(MSDA_ERR_SHAPE, "lqe: bad size B=%d P=%d map %dx%d", B, P, Hf, Wf);
+    if (!msda::lqe_supported(C, K))
+        return fail(MSDA_ERR_SHAPE, "lqe: C=%d (128, 256, 384, 512) or K=%d (1..8) unsupported", C, K);
+    if (coord_mode != MSDA_COORD_UNFUSED && coord_mode != MSDA_COORD_FMA)
+        return fail(MSDA_ERR_SHAPE, "lqe: unknown coord_mode %d", coord_mode);
+    for (int i = 0; i < 4; ++i)
+        if (strides[i] < 0) return fail(MSDA_ERR_SHAPE, "lqe: negative feat stride");
+    if (reinterpret_cast<uintptr_t>(poses) & 7u) return fail(MSDA_ERR_ALIGN, "lqe: poses must be 8-byte aligned");
+    return MSDA_OK;
+}
+}  // namespace
+
+MSDA_API int msda_b200_lqe_forward(const void* feat, int feat_dtype, const int64_t* feat_strides, const float* poses,
+                                   float* stat, int32_t* topk_idx, int B, int C, int Hf, int Wf, int P, int K,
+                                   int coord_mode, void* stream) {
+    if (int rc = check_lqe(feat, feat_dtype, feat_strides, poses, B, C, Hf, Wf, P, K, coord_mode)) return rc;
+    if (stat == nullptr) return fail(MSDA_ERR_NULL, "lqe: stat is NULL");
+    const cudaError_t e = msda::lqe_forward(feat, feat_dtype == MSDA_BF16, feat_strides, poses, stat, topk_idx, B, C,
+                                            Hf, Wf, P, K, coord_mode, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "lqe forward launch");
+}
+
+MSDA_API int msda_b200_lqe_backward(const void* feat, int feat_dtype, const int64_t* feat_strides, const float* poses,
+                                    const int32_t* topk_idx, const float* grad_stat, float* grad_feat,
+                                    float* grad_poses, int B, int C, int Hf, int Wf, int P, int K, int coord_mode,
+                                    void* stream) {
+    if (int rc = check_lqe(feat, feat_dtype, feat_strides, poses, B, C, Hf, Wf, P, K, coord_mode)) return rc;
+    if (topk_idx == nullptr || grad_stat == nullptr) return fail(MSDA_ERR_NULL, "lqe backward: NULL topk_idx / grad_stat");
+    if (reinterpret_cast<uintptr_t>(grad_poses) & 7u) return fail(MSDA_ERR_ALIGN, "lqe: grad_poses must be 8-byte aligned");
+    const cudaError_t e = msda::lqe_backward(feat, feat_dtype == MSDA_BF16, feat_strides, poses, topk_idx, grad_stat,
+                                             grad_feat, grad_poses, B, C, Hf, Wf, P, K, coord_mode,
+                                             (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "lqe backward launch");
+}
+
 }  // extern "C"

@@ -57,4 +57,13 @@ cudaError_t gate_backward(const void* pre, bool pre_bf16, const void* x1, const 
                           const float* gamma, const float* stats, const void* gy, void* gpre, void* gx1, void* gx2,
                           float* ggamma, float* gbeta, int64_t rows, int C, int sm_count, cudaStream_t st);
 
+// msda_lqe.cu
+bool lqe_supported(int C, int K);
+cudaError_t lqe_forward(const void* feat, bool feat_bf16, const int64_t* strides, const float* poses, float* stat,
+                        int32_t* topk_idx, int B, int C, int Hf, int Wf, int P, int K, int coord_mode,
+                        cudaStream_t st);
+cudaError_t lqe_backward(const void* feat, bool feat_bf16, const int64_t* strides, const float* poses,
+                         const int32_t* topk_idx, const float* grad_stat, float* grad_feat, float* grad_poses,
+                         int B, int C, int Hf, int Wf, int P, int K, int coord_mode, cudaStream_t st);
+
 }  // namespace msda

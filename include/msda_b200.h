@@ -204,6 +204,36 @@ MSDA_API int msda_b200_gate_backward(const void* pre, int pre_dtype, const void*
                             void* grad_pre, void* grad_x1, void* grad_x2,
                             float* grad_gamma, float* grad_beta, int64_t rows, int C, void* stream);
 
+/*
+ * LQE sampler -- replaces transformer.py:278-284 (grid_sample of the finest
+ * feature map at the predicted keypoints, permute, top-k over channels, mean, cat):
+ *   stat[b, p, 0..K-1] = the K largest of { bilinear(feat[b, c], poses[b, p]) : c < C }, descending
+ *   stat[b, p, K]      = their mean
+ *
+ * feat          device (B, C, Hf, Wf), feat_dtype, addressed through feat_strides (host[4], elements):
+ *               NCHW and channels-last tensors are both read in place
+ * poses         device fp32 (B, P, 2), normalised (x, y) as in the sampler (pixel = pose * size - 0.5,
+ *               zero padding per corner); P = queries * keypoints
+ * stat          device fp32 (B, P, K + 1)
+ * topk_idx      device int32 (B, P, K): channel of each kept value (lowest channel on ties), needed by
+ *               the backward; may be NULL
+ * C in {128, 256, 384, 512}, 1 <= K <= 8.
+ */
+MSDA_API int msda_b200_lqe_forward(const void* feat, int feat_dtype, const int64_t* feat_strides,
+                          const float* poses, float* stat, int32_t* topk_idx,
+                          int B, int C, int Hf, int Wf, int P, int K, int coord_mode, void* stream);
+
+/*
+ * Backward of the LQE sampler.  grad_stat fp32 (B, P, K+1).
+ * grad_feat   device fp32 with feat's shape AND strides; the gradient is ADDED (the caller zero-fills
+ *             or accumulates; scalar fp32 atomics, 4*K per keypoint); may be NULL
+ * grad_poses  device fp32 (B, P, 2), overwritten; may be NULL
+ */
+MSDA_API int msda_b200_lqe_backward(const void* feat, int feat_dtype, const int64_t* feat_strides,
+                           const float* poses, const int32_t* topk_idx, const float* grad_stat,
+                           float* grad_feat, float* grad_poses,
+                           int B, int C, int Hf, int Wf, int P, int K, int coord_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,44 @@ def run_gate(T, cfg, seed, dtype):
     return inputs, out
 
 
+LQE_CASES = {
+    # name: B, L (queries), keypoints, C, map (Hf, Wf), pose range
+    "small":   dict(B=2, L=3, nb=17, C=128, hw=(6, 8), lo=-0.1, hi=1.1),
+    "s_like":  dict(B=1, L=4, nb=17, C=256, hw=(10, 10), lo=0.0, hi=1.0),
+    "outside": dict(B=1, L=2, nb=5, C=128, hw=(4, 5), lo=-1.5, hi=2.5),
+}
+
+
+def run_lqe(T, cfg, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    B, L, nb, C, (hf, wf) = cfg["B"], cfg["L"], cfg["nb"], cfg["C"], cfg["hw"]
+    k, hidden = 4, 32
+    lqe = T.LQE(k, hidden, 2, nb)
+    last_init = (lqe.reg_conf.layers[-1].weight.detach().abs().max(), lqe.reg_conf.layers[-1].bias.detach().abs().max())
+    with torch.no_grad():
+        for layer in lqe.reg_conf.layers:
+            layer.weight.copy_(torch.randn(layer.weight.shape, generator=g) / layer.weight.shape[1] ** 0.5)
+            layer.bias.copy_(0.1 * torch.randn(layer.bias.shape, generator=g))
+    feat = torch.randn(B, C, hf, wf, generator=g)
+    poses = torch.rand(B, L, nb * 2, generator=g) * (cfg["hi"] - cfg["lo"]) + cfg["lo"]
+    scores = torch.randn(B, L, 1, generator=g)
+    gout = torch.randn(B, L, 1, generator=g)
+    params = {kk: v.detach().clone() for kk, v in lqe.state_dict().items()}
+    lqe = lqe.to(dtype)
+    f, p, sc = (t.to(dtype).requires_grad_(True) for t in (feat, poses, scores))
+    captured = {}
+    lqe.reg_conf.register_forward_hook(lambda m, inp, out: captured.__setitem__("stat", inp[0].detach().clone()))
+    out = lqe(sc, p, f)
+    grads = torch.autograd.grad(out, [f, p, sc, *lqe.parameters()], gout.to(dtype))
+    res = {"out": out, "stat": captured["stat"], "grad_feat": grads[0], "grad_poses": grads[1], "grad_scores": grads[2]}
+    for (n, _), t in zip(lqe.named_parameters(), grads[3:]):
+        res["grad_" + n.replace(".", "_")] = t
+    inputs = dict(feat=feat, poses=poses, scores=scores, grad_out=gout, topk=np.int32(k), num_body_points=np.int32(nb),
+                  init_last_absmax=np.float32(max(float(last_init[0]), float(last_init[1]))))
+    inputs.update({"param_" + kk.replace(".", "_"): v for kk, v in params.items()})
+    return inputs, res
+
+
 def main():
     if not os.path.exists(REF_SRC):
         sys.exit("reference not present: golden vectors can only be regenerated in the build container")
@@ -113,6 +151,16 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"gate_{name}.npz"),
                             **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else v) for k, v in blob.items()})
         print(f"gate_{name}: y {tuple(r32['y'].shape)} |y|max {r32['y'].abs().max():.4f}")
+    for i, (name, cfg) in enumerate(LQE_CASES.items()):
+        inputs, r32 = run_lqe(T, cfg, 900 + i, torch.float32)
+        _, r64 = run_lqe(T, cfg, 900 + i, torch.float64)
+        blob = dict(inputs)
+        for tag, res in (("f32", r32), ("f64", r64)):
+            for k, t in res.items():
+                blob[f"{k}_{tag}"] = t.detach().to(torch.float32)
+        np.savez_compressed(os.path.join(HERE, f"lqe_{name}.npz"),
+                            **{k: (v.detach().numpy() if isinstance(v, torch.Tensor) else v) for k, v in blob.items()})
+        print(f"lqe_{name}: stat {tuple(r32['stat'].shape)} |out|max {r32['out'].abs().max():.4f}")
 
 
 if __name__ == "__main__":

@@ -74,8 +74,8 @@ def test_gate_module_init_and_names():
     from detrpose_b200.gate import Gate
     g = Gate(256)
     assert sorted(g.state_dict()) == ["gate.bias", "gate.weight", "norm.bias", "norm.weight"]
-    assert g.gate.weight.shape == (512, 512) and float(g.gate.weight.abs().max()) == 0.0
-    assert float(g.gate.bias.abs().max()) == 0.0
+    assert g.gate.weight.shape == (512, 512) and float(g.gate.weight.detach().abs().max()) == 0.0
+    assert float(g.gate.bias.detach().abs().max()) == 0.0
     with pytest.raises(ValueError):
         Gate(100)
     with pytest.raises(RuntimeError, match="no CPU path"):
