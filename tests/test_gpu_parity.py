@@ -379,6 +379,42 @@ def test_backward_from_worker_thread_and_non_default_stream():
     assert rel_err(out, c["out_f32"]) <= TOL and rel_err(gm, c["grad_memory_f32"]) <= TOL
 
 
+def test_forward_backward_capture_in_cuda_graph():
+    """The C-ABI calls only enqueue work on the given stream (no allocation, no synchronisation), so a
+    forward + backward pair can be captured once and replayed on new data in the same buffers."""
+    from detrpose_b200 import functional as MF
+    w = synthetic.WORKLOADS["detrpose_s"]
+    mode = MF.get_default_coord_mode()
+
+    def inputs(seed):
+        return synthetic.make_inputs(3, 200, w["H"], w["Dh"], w["shapes"], w["P"], seed=seed, device=DEV,
+                                     value_dtype=torch.bfloat16)
+    a = inputs(1)
+    pyr = MF.pack_value(a["memory"], w["shapes"], w["H"]).clone()
+    loc, attn, go = a["locations"].clone(), a["attention"].clone(), a["grad_out"].clone()
+    s = torch.cuda.Stream(device=DEV)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):                                   # warm-up outside the capture
+            out = MF._forward_raw(pyr, w["shapes"], loc, attn, torch.bfloat16, mode)
+            gv, gl, ga = MF._backward_raw(pyr, w["shapes"], loc, attn, go, True, True, mode)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = MF._forward_raw(pyr, w["shapes"], loc, attn, torch.bfloat16, mode)
+        gv, gl, ga = MF._backward_raw(pyr, w["shapes"], loc, attn, go, True, True, mode)
+    b = inputs(2)
+    pyr.copy_(MF.pack_value(b["memory"], w["shapes"], w["H"]))
+    loc.copy_(b["locations"]); attn.copy_(b["attention"]); go.copy_(b["grad_out"])
+    graph.replay()
+    torch.cuda.synchronize()
+    want_out = MF._forward_raw(pyr, w["shapes"], loc, attn, torch.bfloat16, mode)
+    want = MF._backward_raw(pyr, w["shapes"], loc, attn, go, True, True, mode)
+    assert torch.equal(out, want_out)
+    for x, y in zip((gv, gl, ga), want):
+        assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= 1e-6
+
+
 def test_error_behaviour_on_device():
     loc = torch.rand(1, 2, 2, 1, 2, 2, device=DEV)
     att = torch.full((1, 2, 2, 1, 2), 0.5, device=DEV)
