@@ -236,6 +236,7 @@ def run_b200_arm(args):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = shard.bind_to_gpu_numa(local_rank)      # before any pinned allocation (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -383,6 +384,7 @@ def run_b200_arm(args):
         e2e = {"value": round(e2e_bytes / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": round(e2e_ms / e2e_steps, 3),
+               "cpu_affinity": affinity,
                "api": "detrpose_b200.ms_deform_attn_core + torch.autograd.grad; pinned host buffers, "
                       "upload / compute / download on separate streams, double-buffered"}
 

@@ -16,7 +16,7 @@ from typing import List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["image_range", "local_images", "shard_batch", "job_total", "max_over_ranks", "gather_rows"]
+__all__ = ["image_range", "local_images", "shard_batch", "job_total", "max_over_ranks", "gather_rows", "bind_to_gpu_numa"]
 
 
 def image_range(n_images: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -77,3 +77,31 @@ def gather_rows(local: torch.Tensor, n_images: int, group=None) -> torch.Tensor:
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded, group=group)
     return torch.cat([p[:c] for p, c in zip(parts, counts)], dim=0)
+
+
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (one process
+    per GPU): pinned host buffers are then first-touched on the GPU's own NUMA node, which is what keeps the
+    host<->device copies of N ranks from sharing one memory controller.  Returns a short description;
+    never raises (no NVML, no permission: the process keeps its affinity)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device_index
+        if visible:
+            entry = visible.split(",")[device_index].strip()
+            if entry.isdigit():
+                index = int(entry)
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "unchanged (no overlap with the allowed CPUs)"
+        os.sched_setaffinity(0, allowed)
+        return f"nvml-local cores of GPU {index} ({len(allowed)} cpus)"
+    except Exception as exc:                      # noqa: BLE001 - diagnostics only
+        return f"unchanged ({type(exc).__name__})"
