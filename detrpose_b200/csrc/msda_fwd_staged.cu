@@ -64,10 +64,12 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
     constexpr int E = Vec<VBF>::kElems;
     constexpr int E2 = E / 2;
     constexpr int ES = VBF ? 2 : 4;
-    constexpr int IPC = kStagedThreads / G;          // items (queries of this head) per pass
+    constexpr int IPW = 32 / G;                      // items (queries of this head) a warp handles at a time
+    constexpr int NWARPS = kStagedThreads / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
+    const int lane32 = tid & 31, wid = tid >> 5;
     const int LP = pb.L * pb.P;
     const int part = blockIdx.x % plan.parts;
     const int h = (blockIdx.x / plan.parts) % pb.H;
@@ -77,13 +79,15 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
     const uint32_t row_bytes = (uint32_t)(pb.vs_s * ES);          // global row pitch
     const uint32_t srow_bytes = (uint32_t)(pb.Dh * ES);           // staged row pitch (dense)
 
-    unsigned char* params = smem_raw + plan.stage_bytes;
     const int item_stride = LP * 32 + 16;
+    unsigned char* params = smem_raw + plan.stage_bytes + wid * (IPW * item_stride);   // this warp's table
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const uint32_t bar = sbase + plan.stage_bytes + IPC * item_stride;
+    const uint32_t bar = sbase + plan.stage_bytes + NWARPS * IPW * item_stride;
+    int* work = reinterpret_cast<int*>(smem_raw + plan.stage_bytes + NWARPS * IPW * item_stride + 8);
 
     // ---- start the TMA staging of the coarse levels of (n, h) ----
     if (tid == 0) {
+        *work = 0;
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (uint32_t)plan.n_boxes * kBoxRows * srow_bytes);
         for (int l = plan.first_staged; l < pb.L; ++l) {
@@ -92,22 +96,29 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
                 tma_load_4d(sbase + plan.smem_off[l] + r * srow_bytes, &tmap, 0, h, pb.geom.start[l] + r, n, bar);
         }
     }
-    __syncthreads();                                  // barrier initialised before anyone waits on it
+    __syncthreads();                                  // barrier and work counter initialised
 
     const int lane = tid % G;
-    const int il = tid / G;
+    const int il = lane32 / G;
     const char* vbase = value + ((int64_t)n * pb.vs_n + (int64_t)h * pb.vs_h + lane * E) * ES;
     const uint32_t a_stage = sbase + lane * E * ES;
     bool staged_ready = false;
 
-    for (int q0 = q_begin; q0 < q_end; q0 += IPC) {
-        const int nitems = min(IPC, q_end - q0);
-        // ---- phase 1: one thread per sample of this pass ----
+    // Warps work independently (no CTA-wide barrier after this point): each fetches groups of IPW queries,
+    // builds the sample parameters of its group in its own table and gathers, so that the parameter
+    // loads, the L2 gathers of the finest level and the shared-memory gathers of different warps overlap.
+    for (;;) {
+        int grp = 0;
+        if (lane32 == 0) grp = atomicAdd(work, 1);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        const int q0 = q_begin + grp * IPW;
+        if (q0 >= q_end) break;
+        const int nitems = min(IPW, q_end - q0);
+        // ---- phase 1: the lanes of the warp share the samples of its group ----
         {
             const int nsamp = nitems * LP;
-            int i_l = tid / LP, sl = tid - i_l * LP;
-            const int dil = kStagedThreads / LP, dsl = kStagedThreads - dil * LP;
-            for (int s = tid; s < nsamp; s += kStagedThreads) {
+            for (int s = lane32; s < nsamp; s += 32) {
+                const int i_l = s / LP, sl = s - i_l * LP;
                 const int64_t sidx = (((int64_t)n * pb.Lq + q0 + i_l) * pb.H + h) * LP + sl;
                 const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
                 const float a = __ldg(attn + sidx);
@@ -122,16 +133,14 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
                 const uint32_t r0 = base + (uint32_t)(yc0 * Wl) * pitch, r1 = base + (uint32_t)(yc1 * Wl) * pitch;
                 unsigned char* dst = params + i_l * item_stride + sl * 32;
                 reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
-                reinterpret_cast<uint4*>(dst)[1] = make_uint4(
-                    (sm.vx0 && sm.vy0) ? r0 + xc0 * pitch : 0xffffffffu,
-                    (sm.vx1 && sm.vy0) ? r0 + xc1 * pitch : 0xffffffffu,
-                    (sm.vx0 && sm.vy1) ? r1 + xc0 * pitch : 0xffffffffu,
-                    (sm.vx1 && sm.vy1) ? r1 + xc1 * pitch : 0xffffffffu);
-                i_l += dil; sl += dsl;
-                if (sl >= LP) { sl -= LP; ++i_l; }
+                // Corners outside the map keep an exact zero weight and point at the clamped pixel, which is a
+                // valid corner of the same sample whenever the sample touches the map at all: no predicated
+                // loads in phase 2.  (A sample entirely outside multiplies a border row by zero.)
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(r0 + xc0 * pitch, r0 + xc1 * pitch,
+                                                              r1 + xc0 * pitch, r1 + xc1 * pitch);
             }
         }
-        __syncthreads();
+        __syncwarp();
         if (!staged_ready) { mbar_wait(bar, 0); staged_ready = true; }
 
         // ---- phase 2: G lanes per item gather (shared memory for staged levels) and accumulate ----
@@ -140,50 +149,57 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
 #pragma unroll
             for (int c = 0; c < K * E2; ++c) acc[c] = make_float2(0.0f, 0.0f);
             const unsigned char* ip = params + il * item_stride;
+            // one pair of samples: 8 row loads issued before the first use, then FFMA2 accumulation
+            auto accumulate = [&](const uint4 (&raw)[2][K][4], const float (&wv)[2][4]) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b)
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float2 f[E2];
+                            const uint4 r = raw[b][k][c];
+                            if constexpr (VBF) {
+                                f[0] = make_float2(bf16_lo(r.x), bf16_hi(r.x));
+                                f[1] = make_float2(bf16_lo(r.y), bf16_hi(r.y));
+                                f[2] = make_float2(bf16_lo(r.z), bf16_hi(r.z));
+                                f[3] = make_float2(bf16_lo(r.w), bf16_hi(r.w));
+                            } else {
+                                f[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
+                                f[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
+                            }
+                            const float2 ww = make_float2(wv[b][c], wv[b][c]);
+#pragma unroll
+                            for (int e = 0; e < E2; ++e) acc[k * E2 + e] = __ffma2_rn(f[e], ww, acc[k * E2 + e]);
+                        }
+            };
+            auto pair = [&](const int s, const bool two, auto load_row) {
+                float wv[2][4];
+                uint4 raw[2][K][4];
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    // an odd tail repeats the previous sample with zero weights
+                    const unsigned char* e = ip + (s + ((b == 0 || two) ? b : 0)) * 32;
+                    const float4 w = reinterpret_cast<const float4*>(e)[0];
+                    const uint4 o = reinterpret_cast<const uint4*>(e)[1];
+                    const bool live = b == 0 || two;
+                    wv[b][0] = live ? w.x : 0.0f; wv[b][1] = live ? w.y : 0.0f;
+                    wv[b][2] = live ? w.z : 0.0f; wv[b][3] = live ? w.w : 0.0f;
+                    const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) raw[b][k][c] = load_row(ov[c] + k * G * 16);
+                }
+                accumulate(raw, wv);
+            };
             for (int l = 0; l < pb.L; ++l) {
-                const bool staged = l >= plan.first_staged;
-                for (int p = 0; p < pb.P; p += 2) {
-                    float wv[2][4];
-                    uint4 raw[2][K][4];
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const bool live = p + b < pb.P;
-                        const int s = l * pb.P + p + b;
-                        const float4 w = live ? reinterpret_cast<const float4*>(ip + s * 32)[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const uint4 o = live ? reinterpret_cast<const uint4*>(ip + s * 32)[1]
-                                             : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-                        wv[b][0] = w.x; wv[b][1] = w.y; wv[b][2] = w.z; wv[b][3] = w.w;
-                        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                if (ov[c] == 0xffffffffu) raw[b][k][c] = make_uint4(0, 0, 0, 0);
-                                else if (staged) raw[b][k][c] = lds_u4s(a_stage + ov[c] + k * G * 16);
-                                else raw[b][k][c] = ldg_nc_v4(vbase + ov[c] + k * G * 16);
-                            }
-                    }
-#pragma unroll
-                    for (int b = 0; b < 2; ++b)
-#pragma unroll
-                        for (int k = 0; k < K; ++k)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                float2 f[E2];
-                                const uint4 r = raw[b][k][c];
-                                if constexpr (VBF) {
-                                    f[0] = make_float2(bf16_lo(r.x), bf16_hi(r.x));
-                                    f[1] = make_float2(bf16_lo(r.y), bf16_hi(r.y));
-                                    f[2] = make_float2(bf16_lo(r.z), bf16_hi(r.z));
-                                    f[3] = make_float2(bf16_lo(r.w), bf16_hi(r.w));
-                                } else {
-                                    f[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
-                                    f[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
-                                }
-                                const float2 ww = make_float2(wv[b][c], wv[b][c]);
-#pragma unroll
-                                for (int e = 0; e < E2; ++e) acc[k * E2 + e] = __ffma2_rn(f[e], ww, acc[k * E2 + e]);
-                            }
+                if (l >= plan.first_staged) {                     // warp-uniform: rows of this level are staged
+                    for (int p = 0; p < pb.P; p += 2)
+                        pair(l * pb.P + p, p + 1 < pb.P, [&](const uint32_t o) { return lds_u4s(a_stage + o); });
+                } else {
+                    for (int p = 0; p < pb.P; p += 2)
+                        pair(l * pb.P + p, p + 1 < pb.P, [&](const uint32_t o) { return ldg_nc_v4(vbase + o); });
                 }
             }
             constexpr int OS = OBF ? 2 : 4;
@@ -211,7 +227,7 @@ fwd_staged_kernel(const __grid_constant__ CUtensorMap tmap, const Problem pb, co
                 }
             }
         }
-        __syncthreads();                              // parameters are overwritten by the next pass
+        __syncwarp();                                 // the table is overwritten by the warp's next group
     }
     if (!staged_ready) mbar_wait(bar, 0);             // never leave with the bulk copies in flight
 }
@@ -244,7 +260,7 @@ bool make_stage_plan(const Problem& pb, bool value_bf16, int G, bool small, Stag
     const int srow = pb.Dh * es;
     const int threads = small ? 256 : 768;
     const int ipc = threads / G;
-    const int params_bytes = ipc * (pb.L * pb.P * 32 + 16) + 16;
+    const int params_bytes = ipc * (pb.L * pb.P * 32 + 16) + 16;      // one table of 32 / G items per warp
     const int budget = (small ? kMaxSmemStaged / 4 : kMaxSmemStaged) - params_bytes - 256;
     // stage the longest suffix of levels that fits
     int first = pb.L, bytes = 0;
