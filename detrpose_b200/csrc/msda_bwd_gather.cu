@@ -181,10 +181,13 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     unsigned char* order_s = smem + lay.off_order + warp * 32;           // lane holding the pixel of rank r
     int* work_s = reinterpret_cast<int*>(smem + lay.off_order + 32 * 32);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t a_g = sbase + lay.off_g + lane * 16;                  // this lane's vector of g row 0
-    const uint32_t a_rec = sbase + lay.off_rec;
-    const uint32_t a_dots = sbase + lay.off_dots;
+    uint32_t a_g = sbase + lay.off_g + lane * 16;                        // this lane's vector of g row 0
+    uint32_t a_rec = sbase + lay.off_rec;
+    uint32_t a_dots = sbase + lay.off_dots;
     const uint32_t a_ends = sbase + lay.off_bins;
+    // keep the three bases the visit loop uses in registers: left alone, the compiler rebuilds them from the
+    // shared-window base and the kernel parameters (S2UR / ULEA / LDC) inside the loop
+    asm volatile("" : "+r"(a_g), "+r"(a_rec), "+r"(a_dots));
 
     const char* vlevel = value + ((int64_t)n * pb.vs_n + (int64_t)pb.geom.start[l] * pb.vs_s +
                                   (int64_t)h * pb.vs_h + lane * E) * ES;
@@ -426,11 +429,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     // Cooperative decode: in a batch of 4 visits lane i of the group decodes visit i (record,
                     // weight, g-row address, dot slot); weight and address are then broadcast inside the
                     // group, and after the transpose-reduce lane i holds the dot of the visit it decoded.
-                    const uint32_t a_g0 = a_g - lane * 16;                    // g row 0, vector 0
+                    // (the broadcast address is the byte offset of the g row; every lane adds its own a_g)
                     for (int t = 0; t < trips; t += 4, j += 4 * split) {
                         const int jm = j + lane * split;
                         float w_m = 0.0f;
-                        uint32_t ga_m = a_g0 + qc * (VPR * 16), slot_m = 0u;      // idle slot: zero row, zero weight
+                        uint32_t ga_m = qc * (VPR * 16), slot_m = 0u;             // idle slot: zero row, zero weight
                         if (jm < total) {
                             const bool up = jm < n_up;
                             const int e = jm + (up ? e0_up : delta_dn);
@@ -439,7 +442,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             w_m = (up ? rec.x : rec.y) * (isx1 ? rec.z : 1.0f - rec.z);
                             const unsigned id = __float_as_uint(rec.w);
                             slot_m = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
-                            ga_m = a_g0 + ((id >> 16) & 0xfffu) * (VPR * 16);
+                            ga_m = ((id >> 16) & 0xfffu) * (VPR * 16);
                         }
                         float d[4];
 #pragma unroll
@@ -452,7 +455,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
 #pragma unroll
                                 for (int k = 0; k < K; ++k) {
                                     float2 g[E2];
-                                    unpack2<VBF>(lds_u4(ga + (k * G + lane) * 16), g);
+                                    unpack2<VBF>(lds_u4(a_g + ga + k * G * 16), g);
 #pragma unroll
                                     for (int c = 0; c < E2; ++c) {
                                         if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
