@@ -145,24 +145,39 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
         const float* asrc = attn + item0 * LP;
         int il = tid / LP, sl = tid - il * LP;       // item inside the CTA, sample inside the item
         const int dil = kFwdThreads / LP, dsl = kFwdThreads - dil * LP;
-        for (int s = tid; s < nsamp; s += kFwdThreads) {
-            const float2 xy = __ldg(lsrc + s);
-            const float a = __ldg(asrc + s);
-            const int l = sl / pb.P;
-            const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
-            const Sample sm = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
-            const int xc0 = min(max(sm.x0, 0), Wl - 1), xc1 = min(max(sm.x0 + 1, 0), Wl - 1);
-            const int yc0 = min(max(sm.y0, 0), Hl - 1), yc1 = min(max(sm.y0 + 1, 0), Hl - 1);
-            const uint32_t r0 = (uint32_t)(pb.geom.start[l] + yc0 * Wl), r1 = (uint32_t)(pb.geom.start[l] + yc1 * Wl);
-            unsigned char* dst = smem_raw + il * item_stride + sl * 32;
-            reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
-            reinterpret_cast<uint4*>(dst)[1] = make_uint4(
-                (sm.vx0 && sm.vy0) ? (r0 + xc0) * row_bytes : 0xffffffffu,
-                (sm.vx1 && sm.vy0) ? (r0 + xc1) * row_bytes : 0xffffffffu,
-                (sm.vx0 && sm.vy1) ? (r1 + xc0) * row_bytes : 0xffffffffu,
-                (sm.vx1 && sm.vy1) ? (r1 + xc1) * row_bytes : 0xffffffffu);
-            il += dil; sl += dsl;
-            if (sl >= LP) { sl -= LP; ++il; }
+        // the loads of up to three samples are issued before the first dependent instruction: one exposed
+        // DRAM latency per batch instead of one per sample (a thread has 3 samples for G = 4, 6 for G = 2)
+        constexpr int PF = 3;
+        for (int s0 = tid; s0 < nsamp; s0 += PF * kFwdThreads) {
+            float2 xy_[PF];
+            float a_[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int s = s0 + u * kFwdThreads;
+                xy_[u] = s < nsamp ? __ldg(lsrc + s) : make_float2(0.0f, 0.0f);
+                a_[u] = s < nsamp ? __ldg(asrc + s) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (s0 + u * kFwdThreads >= nsamp) break;
+                const float2 xy = xy_[u];
+                const float a = a_[u];
+                const int l = sl / pb.P;
+                const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
+                const Sample sm = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
+                const int xc0 = min(max(sm.x0, 0), Wl - 1), xc1 = min(max(sm.x0 + 1, 0), Wl - 1);
+                const int yc0 = min(max(sm.y0, 0), Hl - 1), yc1 = min(max(sm.y0 + 1, 0), Hl - 1);
+                const uint32_t r0 = (uint32_t)(pb.geom.start[l] + yc0 * Wl), r1 = (uint32_t)(pb.geom.start[l] + yc1 * Wl);
+                unsigned char* dst = smem_raw + il * item_stride + sl * 32;
+                reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(
+                    (sm.vx0 && sm.vy0) ? (r0 + xc0) * row_bytes : 0xffffffffu,
+                    (sm.vx1 && sm.vy0) ? (r0 + xc1) * row_bytes : 0xffffffffu,
+                    (sm.vx0 && sm.vy1) ? (r1 + xc0) * row_bytes : 0xffffffffu,
+                    (sm.vx1 && sm.vy1) ? (r1 + xc1) * row_bytes : 0xffffffffu);
+                il += dil; sl += dsl;
+                if (sl >= LP) { sl -= LP; ++il; }
+            }
         }
     }
     __syncthreads();
