@@ -114,7 +114,7 @@ fwd_flat_kernel(const Problem pb, const char* __restrict__ value,
 // ---------------------------------------------------------------------------
 struct __align__(16) SampleParams {
     float w[4];          // nw, ne, sw, se weight times attention, 0 for dropped corners
-    uint32_t off[4];     // byte offset of the corner row from the (n, h) base; ~0u: dropped corner
+    uint32_t off[4];     // byte offset of the (clamped) corner row from the (n, h) base; off[0] == ~0u: no valid corner
 };
 
 template <int G, int K, bool VBF, bool OBF, int MINB>
@@ -170,11 +170,14 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 const uint32_t r0 = (uint32_t)(pb.geom.start[l] + yc0 * Wl), r1 = (uint32_t)(pb.geom.start[l] + yc1 * Wl);
                 unsigned char* dst = smem_raw + il * item_stride + sl * 32;
                 reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
-                reinterpret_cast<uint4*>(dst)[1] = make_uint4(
-                    (sm.vx0 && sm.vy0) ? (r0 + xc0) * row_bytes : 0xffffffffu,
-                    (sm.vx1 && sm.vy0) ? (r0 + xc1) * row_bytes : 0xffffffffu,
-                    (sm.vx0 && sm.vy1) ? (r1 + xc0) * row_bytes : 0xffffffffu,
-                    (sm.vx1 && sm.vy1) ? (r1 + xc1) * row_bytes : 0xffffffffu);
+                // A corner outside the map keeps an exact zero weight and points at the clamped pixel, which is
+                // a VALID corner of the same sample whenever the sample touches the map at all (so the result,
+                // Inf/NaN propagation included, is what per-corner dropping gives); a sample with no valid
+                // corner is flagged and skipped as a whole.  One predicate per sample instead of one per corner.
+                const bool any = (sm.vx0 | sm.vx1) & (sm.vy0 | sm.vy1);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(any ? (r0 + xc0) * row_bytes : 0xffffffffu,
+                                                              (r0 + xc1) * row_bytes, (r1 + xc0) * row_bytes,
+                                                              (r1 + xc1) * row_bytes);
                 il += dil; sl += dsl;
                 if (sl >= LP) { sl -= LP; ++il; }
             }
@@ -204,23 +207,26 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     for (int s = 0; s < LP; s += B) {
         float wv[B][4];
         uint4 raw[B][K][4];
+        bool live[B];
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-            const bool live = s + b < LP;
-            const float4 w = live ? reinterpret_cast<const float4*>(ip + (s + b) * 32)[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint4 o = live ? reinterpret_cast<const uint4*>(ip + (s + b) * 32)[1]
-                                 : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            const bool in = s + b < LP;                                  // odd tail: re-reads the previous entry
+            const unsigned char* e = ip + (in ? s + b : s) * 32;
+            const float4 w = reinterpret_cast<const float4*>(e)[0];
+            const uint4 o = reinterpret_cast<const uint4*>(e)[1];
             wv[b][0] = w.x; wv[b][1] = w.y; wv[b][2] = w.z; wv[b][3] = w.w;
+            live[b] = in && o.x != 0xffffffffu;                          // sample with at least one valid corner
             const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+            if (live[b]) {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
+                for (int k = 0; k < K; ++k)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    raw[b][k][c] = ov[c] != 0xffffffffu ? ldg_nc_v4(vbase + ov[c] + k * G * 16)
-                                                        : make_uint4(0, 0, 0, 0);
+                    for (int c = 0; c < 4; ++c) raw[b][k][c] = ldg_nc_v4(vbase + ov[c] + k * G * 16);
+            }
         }
 #pragma unroll
-        for (int b = 0; b < B; ++b)
+        for (int b = 0; b < B; ++b) {
+            if (!live[b]) continue;
 #pragma unroll
             for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -238,8 +244,9 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                     }
                     const float2 ww = make_float2(wv[b][c], wv[b][c]);
 #pragma unroll
-                    for (int e = 0; e < E2; ++e) acc[k * E2 + e] = __ffma2_rn(f[e], ww, acc[k * E2 + e]);
+                    for (int e2 = 0; e2 < E2; ++e2) acc[k * E2 + e2] = __ffma2_rn(f[e2], ww, acc[k * E2 + e2]);
                 }
+        }
     }
 
     constexpr int OS = OBF ? 2 : 4;
