@@ -155,6 +155,8 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
     total = sum(h * w for h, w in shapes)
     if isinstance(value, torch.Tensor):
         _require_cuda(value, "value")
+        if value.dtype == torch.float16:         # the reference's AMP is fp16 autocast: its sampler runs fp32
+            value = value.float()
         if value.dim() == 3:
             value = value.unflatten(2, (n_heads, -1))
         if value.dim() != 4 or value.shape[1] != total or value.shape[2] != n_heads:
@@ -170,7 +172,7 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
         _require_cuda(v, "value")
         if v.dim() != 3 or v.shape[2] != h * w or v.shape[:2] != levels[0].shape[:2]:
             raise ValueError(f"value level of shape {tuple(v.shape)} does not match (N*H, Dh, {h}*{w})")
-    view = _zero_copy_view(levels, shapes, n_heads)
+    view = _zero_copy_view(levels, shapes, n_heads) if levels[0].dtype in _DTYPE_CODE else None
     if view is not None:
         return view
     if use_cache:
@@ -182,9 +184,10 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
         raise ValueError(f"value leading dim {nh} is not a multiple of n_heads={n_heads}")
     n = nh // n_heads
     dtype = levels[0].dtype
-    if dtype not in _DTYPE_CODE:                 # e.g. fp16 under the reference's AMP: sampler runs fp32
+    if dtype == torch.float16:                   # the reference's AMP (fp16 autocast): its sampler runs fp32
         levels = [v.float() for v in levels]
         dtype = torch.float32
+    _code(dtype)                                 # anything else but fp32 / bf16: TypeError
     pyramid = torch.empty((n, total, n_heads, dh), dtype=dtype, device=levels[0].device)
     lib = _lib.load()
     with torch.cuda.device(pyramid.device):

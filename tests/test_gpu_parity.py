@@ -415,6 +415,23 @@ def test_forward_backward_capture_in_cuda_graph():
         assert rel_err(x.cpu().numpy(), y.cpu().numpy()) <= 1e-6
 
 
+def test_fp16_inputs_run_the_sampler_in_fp32():
+    """The reference trains under fp16 autocast (engine.py:20), where grid_sample runs in fp32: fp16 value
+    lists / tensors are up-cast, the result is fp32 and matches the fp32 run on the same (fp16-rounded) data."""
+    c = load_core_case("s_like")
+    mem16 = torch.from_numpy(c["memory"]).to(DEV).half()
+    loc = torch.from_numpy(c["locations"]).to(DEV)
+    att = torch.from_numpy(c["attention"]).to(DEV)
+    want = dp.ms_deform_attn_core(mem16.float(), c["shapes"], loc, att, n_heads=c["n_heads"])
+    got_t = dp.ms_deform_attn_core(mem16, c["shapes"], loc.half(), att.half(), n_heads=c["n_heads"])
+    got_l = dp.ms_deform_attn_core(value_list_from_memory(mem16, c["n_heads"], c["shapes"]), c["shapes"], loc, att)
+    assert got_t.dtype == torch.float32 and got_l.dtype == torch.float32
+    assert torch.equal(got_l, want)
+    assert rel_err(got_t.cpu().numpy(), want.cpu().numpy()) < 5e-3       # locations / attention rounded to fp16
+    with pytest.raises(TypeError):
+        dp.ms_deform_attn_core(value_list_from_memory(mem16.double(), c["n_heads"], c["shapes"]), c["shapes"], loc, att)
+
+
 def test_error_behaviour_on_device():
     loc = torch.rand(1, 2, 2, 1, 2, 2, device=DEV)
     att = torch.full((1, 2, 2, 1, 2), 0.5, device=DEV)
