@@ -362,6 +362,20 @@ def sample_indices(sampling_locations: torch.Tensor, spatial_shapes, coord_mode:
     return idx, starts
 
 
+_normalizer_cache: dict = {}
+
+
+def level_normalizer(shapes, device) -> torch.Tensor:
+    """fp32 ``(L, 2)`` tensor of ``(W_l, H_l)`` on ``device``, created once per (shapes, device): building it
+    from a Python list on every call (ms_deform_attn.py:414) is a blocking host-to-device copy."""
+    key = (tuple(tuple(int(d) for d in hw) for hw in shapes), str(device))
+    t = _normalizer_cache.get(key)
+    if t is None:
+        t = torch.tensor([[w, h] for h, w in key[0]], dtype=torch.float32, device=device)
+        _normalizer_cache[key] = t
+    return t
+
+
 class _Prologue(torch.autograd.Function):
     """Fused softmax + location kernel with an analytic backward (elementwise torch ops)."""
 
@@ -385,7 +399,7 @@ class _Prologue(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
             grad_loc = grad_loc.float()
             if ctx.needs_input_grad[0]:
-                norm = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32, device=att.device)
+                norm = level_normalizer(shapes, att.device)
                 g_off = (grad_loc / norm.view(1, 1, 1, n_levels, 1, 2)).reshape(off_shape)
             if ctx.needs_input_grad[2]:
                 g_ref = grad_loc.sum(dim=(2, 4))                       # over heads and points -> (N, Lq, L, 2)

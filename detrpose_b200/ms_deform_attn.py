@@ -101,17 +101,20 @@ class MSDeformAttn(nn.Module):
         if last not in (2, 4):
             raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(last))
 
-        all_f32 = offsets.dtype == logits.dtype == ref.dtype == torch.float32
-        if last == 2 and self.fuse_prologue and all_f32 and offsets.is_cuda:
-            locations, weights = MF.locations_and_weights(offsets, logits, ref, shapes, H, L, P)
+        if last == 2 and self.fuse_prologue and offsets.is_cuda:
+            # one kernel for softmax + locations, in fp32: bit-identical to the reference's ops for fp32
+            # inputs; under autocast (bf16 / fp16 Linear outputs) the arithmetic is done in fp32 instead of
+            # the reduced precision, which only moves the locations closer to the fp32 result
+            locations, weights = MF.locations_and_weights(offsets.float(), logits.float(), ref.float(),
+                                                          shapes, H, L, P)
         else:
             offsets = offsets.view(N, Len_q, H, L, P, 2)
             weights = F.softmax(logits.view(N, Len_q, H, L * P), -1).view(N, Len_q, H, L, P)
             if last == 2:
-                normalizer = torch.tensor([[w, h] for h, w in shapes], device=query.device)
+                normalizer = MF.level_normalizer(shapes, query.device)
                 locations = ref[:, :, None, :, None, :] + offsets / normalizer.reshape(1, 1, 1, L, 1, 2)
             elif self.use_4D_normalizer:
-                normalizer = torch.tensor([[w, h] for h, w in shapes], device=query.device)
+                normalizer = MF.level_normalizer(shapes, query.device)
                 locations = ref[:, :, None, :, None, :2] \
                     + offsets / normalizer[None, None, None, :, None, :] * ref[:, :, None, :, None, 2:] * 0.5
             else:

@@ -442,3 +442,28 @@ def test_error_behaviour_on_device():
     with pytest.raises(TypeError):
         dp.ms_deform_attn_core(torch.randn(1, 16, 16, device=DEV, dtype=torch.float64), [(4, 4)],
                                loc, att, n_heads=2)
+
+
+def test_module_under_bf16_autocast_uses_fused_prologue_and_tracks_fp32():
+    """bf16 autocast (Linear outputs in bf16): the module still takes the fused fp32 prologue, returns the
+    value dtype, back-propagates to query / value / parameters, and stays close to its own fp32 run."""
+    torch.manual_seed(0)
+    m = dp.MSDeformAttn(d_model=256, n_levels=3, n_heads=8, n_points=4).to(DEV)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.05)
+    shapes = [[20, 20], [10, 10], [5, 5]]
+    S = sum(h * w for h, w in shapes)
+    query = torch.randn(2, 36, 256, device=DEV, requires_grad=True)
+    ref = torch.rand(2, 2, 1, 18, 2, device=DEV)
+    memory = torch.randn(2, S, 256, device=DEV, requires_grad=True)
+    want = m(query, ref, memory, shapes)
+    before = dp.functional.stats["forward_launches"]
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        got = m(query, ref, memory.bfloat16(), shapes)
+    assert dp.functional.stats["forward_launches"] == before + 1
+    assert got.dtype == torch.bfloat16
+    assert rel_err(got.float().detach().cpu().numpy(), want.detach().cpu().numpy()) < 0.05
+    got.float().square().mean().backward()
+    assert query.grad is not None and memory.grad is not None and m.sampling_offsets.weight.grad is not None
+    assert torch.isfinite(query.grad).all() and torch.isfinite(memory.grad).all()

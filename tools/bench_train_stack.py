@@ -96,6 +96,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast (bf16 memory) instead of fp32")
+    ap.add_argument("--no-fused-prologue", action="store_true", help="softmax / locations through torch ops")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -115,6 +116,10 @@ def main():
         for m in model.modules():
             if isinstance(m, nn.Linear) and m.weight.abs().max() == 0:
                 m.weight.normal_(0, 0.02)
+    if args.no_fused_prologue:
+        for m in model.modules():
+            if isinstance(m, dp.MSDeformAttn):
+                m.fuse_prologue = False
     ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
 
