@@ -14,7 +14,7 @@ all arithmetic runs in ``libmsda_b200.so``.  There is no fallback path.
 from __future__ import annotations
 
 import weakref
-from typing import List, Sequence, Tuple, Union
+from typing import List, Sequence, Tuple
 
 import torch
 

@@ -14,7 +14,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from detrpose_b200.gate import Gate, gate_epilogue                  # noqa: E402
+from detrpose_b200.gate import Gate                                 # noqa: E402
 from detrpose_b200 import _lib                                      # noqa: E402
 from detrpose_b200.functional import _code, _stream_ptr             # noqa: E402
 
