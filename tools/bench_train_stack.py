@@ -97,6 +97,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--autocast", action="store_true", help="bf16 autocast (bf16 memory) instead of fp32")
     ap.add_argument("--no-fused-prologue", action="store_true", help="softmax / locations through torch ops")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture forward + backward + AdamW of one step in a CUDA graph and replay it (1 GPU)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,7 +123,7 @@ def main():
             if isinstance(m, dp.MSDeformAttn):
                 m.fuse_prologue = False
     ddp = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
-    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
+    opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4, capturable=args.graph)
 
     g = torch.Generator(device=dev).manual_seed(100 + rank)   # each rank its own images
     mdt = torch.bfloat16 if args.autocast else torch.float32
@@ -144,6 +146,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-GPU option")
+        # The C-ABI calls only enqueue work on the current stream (no allocation, no synchronisation), so a
+        # whole training step -- autograd included -- can be captured once and replayed.
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        memory.grad = None
+        with torch.cuda.graph(graph):
+            captured_loss = step()
+        eager_step = step
+
+        def step():                                            # noqa: F811 - the timed loop replays the graph
+            graph.replay()
+            return captured_loss
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -162,7 +186,8 @@ def main():
                 "scaling": "weak", "dtype": "bf16 autocast" if args.autocast else "fp32",
                 "config": {"layers": args.layers, "images_per_gpu": args.batch, "Lq": args.lq, "d_model": C,
                            "levels": shapes, "points": P, "optimizer": "AdamW",
-                           "gradient_sync": "DDP all-reduce (NCCL)" if world > 1 else "none (1 GPU)"},
+                           "gradient_sync": "DDP all-reduce (NCCL)" if world > 1 else "none (1 GPU)",
+                           "cuda_graph": bool(args.graph)},
                 "final_loss": round(loss_v, 6),
                 "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2)}
         sys.stdout.write(json.dumps(line) + "\n")
