@@ -662,9 +662,10 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
                     const int64_t sidx = s0 + q * sstride + v * 4;
                     *reinterpret_cast<float4*>(grad_attn + sidx) = make_float4(r0.x, r1.x, r2.x, r3.x);
-                    float4* gl4 = reinterpret_cast<float4*>(reinterpret_cast<float2*>(grad_loc) + sidx);
-                    gl4[0] = make_float4(r0.y, r0.z, r1.y, r1.z);
-                    gl4[1] = make_float4(r2.y, r2.z, r3.y, r3.z);
+                    // one 32-byte sector per (query, 4 samples): a single 256-bit store
+                    stg_v8(reinterpret_cast<float*>(reinterpret_cast<float2*>(grad_loc) + sidx),
+                           make_float2(r0.y, r0.z), make_float2(r1.y, r1.z), make_float2(r2.y, r2.z),
+                           make_float2(r3.y, r3.z));
                 }
             } else {
                 int q = q_t0, p = p_t0;
