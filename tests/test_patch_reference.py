@@ -79,3 +79,57 @@ def test_drop_in_module_interface_equals_reference_class(ref):
     for (_, a), (_, b) in zip(ours.named_parameters(), theirs.named_parameters()):
         assert a.shape == b.shape and torch.equal(a, b)
     ours.load_state_dict(theirs.state_dict())
+
+
+# ---------------------------------------------------------------------------------------------
+# Gate / LQE patches on the real reference classes (transformer.py:222-235, 263-288)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_transformer():
+    spec = importlib.util.spec_from_file_location(
+        "make_golden_blocks_patch_test", os.path.join(os.path.dirname(__file__), "golden", "make_golden_blocks.py"))
+    mgb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mgb)
+    return mgb.load_reference_transformer()
+
+
+def test_gate_patch_on_reference_class(ref_transformer):
+    from detrpose_b200.gate import install_gate, uninstall_gate, Gate
+    T = ref_transformer
+    m = T.Gate(128)
+    original = T.Gate.forward
+    x1, x2 = torch.randn(2, 3, 128), torch.randn(2, 3, 128)
+    want = m(x1, x2)
+    install_gate(T)
+    try:
+        assert T.Gate.forward is not original
+        assert torch.equal(m(x1, x2), want)                  # CPU tensors: the reference's own forward
+    finally:
+        uninstall_gate(T)
+    assert T.Gate.forward is original
+    # the drop-in class loads the reference's state_dict and starts from the reference's initialisation
+    ours = Gate(128)
+    assert sorted(ours.state_dict()) == sorted(m.state_dict())
+    for k, v in m.state_dict().items():
+        assert torch.equal(ours.state_dict()[k], v), k
+    ours.load_state_dict(m.state_dict())
+
+
+def test_lqe_patch_on_reference_class(ref_transformer):
+    from detrpose_b200.lqe import install_lqe, uninstall_lqe, LQE
+    T = ref_transformer
+    m = T.LQE(4, 32, 2, 17)
+    original = T.LQE.forward
+    scores, poses, feat = torch.randn(1, 3, 1), torch.rand(1, 3, 34), torch.randn(1, 128, 6, 5)
+    want = m(scores, poses, feat)
+    install_lqe(T)
+    try:
+        assert torch.equal(m(scores, poses, feat), want)     # CPU tensors: the reference's own forward
+    finally:
+        uninstall_lqe(T)
+    assert T.LQE.forward is original
+    ours = LQE(4, 32, 2, 17)
+    assert sorted(ours.state_dict()) == sorted(m.state_dict())
+    assert [tuple(v.shape) for _, v in sorted(ours.state_dict().items())] == \
+           [tuple(v.shape) for _, v in sorted(m.state_dict().items())]
+    ours.load_state_dict(m.state_dict())
