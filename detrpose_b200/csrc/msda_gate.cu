@@ -89,7 +89,9 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
-__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// ex2.approx + rcp.approx (about 2 ulp each): the IEEE division alone was a third of the kernel's instructions
+// and made the bf16 variant issue-bound
+__device__ __forceinline__ float sigmoidf(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 template <bool PBF, bool XBF, int EPL>
 __global__ void __launch_bounds__(kGateWarps * 32)
