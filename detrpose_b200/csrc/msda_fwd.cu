@@ -27,8 +27,16 @@ fwd_flat_kernel(const Problem pb, const char* __restrict__ value,
     const int64_t item = ((int64_t)blockIdx.x * kFwdThreads + threadIdx.x) / G;
     const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
     if (item >= items) return;
-    const int h = (int)(item % pb.H);
-    const int n = (int)(item / ((int64_t)pb.H * pb.Lq));
+    // 32-bit division whenever the item index fits (a 64-bit divide is a ~100-instruction subroutine per thread)
+    int h, n;
+    if (items <= 0x7fffffffLL) {
+        const unsigned it = (unsigned)item;
+        h = (int)(it % (unsigned)pb.H);
+        n = (int)(it / ((unsigned)pb.H * (unsigned)pb.Lq));
+    } else {
+        h = (int)(item % pb.H);
+        n = (int)(item / ((int64_t)pb.H * pb.Lq));
+    }
 
     const int LP = pb.L * pb.P;
     const float* locp = loc + item * LP * 2;
@@ -192,8 +200,16 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     // two of lanes with the surplus lanes idle: one request per corner row instead of three
     if (il >= nitems || lane * 16 >= pb.Dh * ES) return;
     const int64_t item = item0 + il;
-    const int h = (int)(item % pb.H);
-    const int n = (int)(item / ((int64_t)pb.H * pb.Lq));
+    // 32-bit division whenever the item index fits (a 64-bit divide is a ~100-instruction subroutine per thread)
+    int h, n;
+    if (items <= 0x7fffffffLL) {
+        const unsigned it = (unsigned)item;
+        h = (int)(it % (unsigned)pb.H);
+        n = (int)(it / ((unsigned)pb.H * (unsigned)pb.Lq));
+    } else {
+        h = (int)(item % pb.H);
+        n = (int)(item / ((int64_t)pb.H * pb.Lq));
+    }
     const char* vbase = value + ((int64_t)n * pb.vs_n + (int64_t)h * pb.vs_h + lane * E) * ES;
 
     float2 acc[K * E2];
