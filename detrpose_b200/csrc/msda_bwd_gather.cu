@@ -98,6 +98,14 @@ __device__ __forceinline__ unsigned lds_u16(uint32_t a) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
     return r;
 }
+__device__ __forceinline__ unsigned lds_u8(uint32_t a) {
+    unsigned r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, unsigned v) {
+    asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) {
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory");
 }
@@ -178,7 +186,6 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     float4* tmp_s = reinterpret_cast<float4*>(smem + lay.off_dots);      // unsorted records live here until P4
     unsigned* bins = reinterpret_cast<unsigned*>(smem + lay.off_bins);
     unsigned* scan_s = reinterpret_cast<unsigned*>(smem + lay.off_scan);
-    unsigned char* order_s = smem + lay.off_order + warp * 32;           // lane holding the pixel of rank r
     int* work_s = reinterpret_cast<int*>(smem + lay.off_order + 32 * 32);
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem);
     uint32_t a_g = sbase + lay.off_g + lane * 16;                        // this lane's vector of g row 0
@@ -187,12 +194,15 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const uint32_t a_ends = sbase + lay.off_bins;
     // keep the three bases the visit loop uses in registers: left alone, the compiler rebuilds them from the
     // shared-window base and the kernel parameters (S2UR / ULEA / LDC) inside the loop
-    asm volatile("" : "+r"(a_g), "+r"(a_rec), "+r"(a_dots));
+    uint32_t a_order = sbase + lay.off_order + warp * 32;                // lane holding the pixel of rank r
+    asm volatile("" : "+r"(a_g), "+r"(a_rec), "+r"(a_dots), "+r"(a_order));
 
     const char* vlevel = value + ((int64_t)n * pb.vs_n + (int64_t)pb.geom.start[l] * pb.vs_s +
                                   (int64_t)h * pb.vs_h + lane * E) * ES;
     const int64_t vrow = pb.vs_s * ES;
     const int64_t gv_row = (int64_t)pb.H * pb.Dh;
+    // byte / element offsets inside one level fit 32 bits (make_plan checks): cheaper address arithmetic
+    const uint32_t vrow32 = (uint32_t)vrow, gv_row32 = (uint32_t)gv_row;
     float* gvlevel = grad_value
         ? grad_value + ((int64_t)n * pb.S + pb.geom.start[l]) * gv_row + (int64_t)h * pb.Dh + lane * E
         : nullptr;
@@ -406,7 +416,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 const bool need = SMALL && u.valid && (int)(u.nt >> 16) > part;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
-                    raw[k] = need ? ldg_nc_v4(vlevel + (int64_t)u.pix * vrow + k * G * 16) : make_uint4(0, 0, 0, 0);
+                    raw[k] = need ? ldg_nc_v4(vlevel + (uint32_t)u.pix * vrow32 + k * G * 16) : make_uint4(0, 0, 0, 0);
             };
 
             auto run = [&](const Unit& u, const int part, const uint4* raw) {
@@ -526,7 +536,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     }
                 }
                 if (gvlevel != nullptr && u.valid && part == 0 && !(rmw && total == 0)) {
-                    float* dst = gvlevel + (int64_t)u.pix * gv_row;
+                    float* dst = gvlevel + (uint32_t)u.pix * gv_row32;
                     if (E == 8 && wide_store) {
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
@@ -574,7 +584,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     int base = 0;
                     for (int c = maxc; c >= 0; --c) {
                         const unsigned m = __ballot_sync(FULL, cnt == c);
-                        if (cnt == c) order_s[base + __popc(m & lt)] = (unsigned char)lane32;
+                        if (cnt == c) sts_u8(a_order + base + __popc(m & lt), (unsigned)lane32);
                         base += __popc(m);
                     }
                     __syncwarp();
@@ -583,7 +593,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                         Unit u;
                         const int r = u0 + gsub;
                         u.valid = r < nvalid;
-                        const int src = u.valid ? (int)order_s[r] : 0;
+                        const int src = u.valid ? (int)lds_u8(a_order + r) : 0;
                         u.eu = __shfl_sync(FULL, eu, src);
                         u.ed = __shfl_sync(FULL, ed, src);
                         u.nt = __shfl_sync(FULL, nt, src);
@@ -720,6 +730,12 @@ static bool make_plan(const Problem& pb, int row_bytes, GatherPlan& plan) {
     int max_bins = 0;
     for (int l = 0; l < pb.L; ++l) max_bins = max(max_bins, (pb.geom.w[l] + 1) * (pb.geom.h[l] + 1));
     plan.bins_words = (max_bins + 3) / 2;
+    // the kernel addresses a level's value rows / gradient rows with 32-bit offsets from the level base
+    const int es = row_bytes / pb.Dh;
+    for (int l = 0; l < pb.L; ++l) {
+        const int64_t npix = (int64_t)pb.geom.w[l] * pb.geom.h[l];
+        if (npix * pb.vs_s * es >= (int64_t)0xffffffffLL || npix * pb.H * pb.Dh >= (int64_t)0x7fffffffLL) return false;
+    }
     const int fixed = align16(plan.bins_words * 4) + 64 * 4 + 32 * 64 * 2 + 16 + row_bytes + 16;
     const int per_query = row_bytes + pb.P * 32;
     int qmax = (kMaxSmem - fixed) / per_query;
