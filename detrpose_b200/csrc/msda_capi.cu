@@ -170,8 +170,11 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
     if (grad_out_dtype != MSDA_F32 && grad_out_dtype != MSDA_BF16)
         return fail(MSDA_ERR_DTYPE, "unknown grad_out dtype %d", grad_out_dtype);
     if (!aligned16(grad_out) || !aligned16(locations) || !aligned16(attention) ||
-        (grad_value && !aligned16(grad_value)) || (grad_locations && !aligned16(grad_locations)))
+        (grad_value && !aligned16(grad_value)) || (grad_attention && !aligned16(grad_attention)))
         return fail(MSDA_ERR_ALIGN, "backward buffers must be 16-byte aligned");
+    // the gather kernel writes grad_locations with one 256-bit store per (query, 4 points)
+    if (grad_locations && (reinterpret_cast<uintptr_t>(grad_locations) & 31u))
+        return fail(MSDA_ERR_ALIGN, "grad_locations must be 32-byte aligned");
     if (!grad_value && !grad_locations) return MSDA_OK;
     const cudaStream_t st = (cudaStream_t)stream;
     const bool vbf = value_dtype == MSDA_BF16;

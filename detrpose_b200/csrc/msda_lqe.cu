@@ -36,6 +36,18 @@ __device__ __forceinline__ float load_elem(const void* base, int64_t off) {
     }
 }
 
+// torch.topk's order (transformer.py:282): NaN counts as the largest value, ties go to the lower channel;
+// a candidate with channel kNone ("this lane has nothing left") loses against everything
+constexpr int kNone = 0x7fffffff;
+__device__ __forceinline__ bool lqe_better(float a, int ca, float b, int cb) {
+    if (cb == kNone) return ca != kNone;
+    if (ca == kNone) return false;
+    const bool an = a != a, bn = b != b;
+    if (an != bn) return an;
+    if (!an && a != b) return a > b;
+    return ca < cb;
+}
+
 struct LqeGeom {
     int64_t sb, sc, sy, sx;     // feat strides in elements
     int B, C, Hf, Wf, P, K, coord_mode;
@@ -68,22 +80,23 @@ lqe_fwd_kernel(const void* __restrict__ feat, const float* __restrict__ poses, f
 
     float sum = 0.0f, mine = 0.0f;
     int mine_c = 0;
+    unsigned taken = 0u;                      // channels of this lane already selected (bit j)
     for (int r = 0; r < gm.K; ++r) {
-        // best of this lane (lowest channel on ties), then arg-max over the warp
-        float bv = -FLT_MAX;
-        int bc = 0x7fffffff;
+        // best of this lane among the channels not taken yet, then arg-max over the warp.  Non-finite
+        // samples are ordinary candidates (NaN first, as torch.topk orders them): the statistics then carry
+        // the NaN / Inf like the reference's do, and every stored index is a real channel.
+        float bv = 0.0f;
+        int bc = kNone;
 #pragma unroll
         for (int j = 0; j < NJ; ++j)
-            if (vals[j] > bv) { bv = vals[j]; bc = j * 32 + lane; }
+            if (!((taken >> j) & 1u) && lqe_better(vals[j], j * 32 + lane, bv, bc)) { bv = vals[j]; bc = j * 32 + lane; }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const float ov = __shfl_xor_sync(kFull, bv, off);
             const int oc = __shfl_xor_sync(kFull, bc, off);
-            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            if (lqe_better(ov, oc, bv, bc)) { bv = ov; bc = oc; }
         }
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-            if (j * 32 + lane == bc) vals[j] = -FLT_MAX;
+        if ((bc & 31) == lane && bc != kNone) taken |= 1u << (bc >> 5);
         sum += bv;
         if (lane == r) { mine = bv; mine_c = bc; }
     }
@@ -115,7 +128,8 @@ lqe_bwd_kernel(const void* __restrict__ feat, const float* __restrict__ poses, c
     if (j < gm.K) {
         const float g = __ldg(grad_stat + pt * (gm.K + 1) + j) + __ldg(grad_stat + pt * (gm.K + 1) + gm.K) / (float)gm.K;
         const int c = __ldg(topk_idx + pt * gm.K + j);
-        const bool valid = (right ? s.vx1 : s.vx0) & (low ? s.vy1 : s.vy0);
+        // an index outside [0, C) cannot come from the forward kernel; never turn one into an address
+        const bool valid = (right ? s.vx1 : s.vx0) & (low ? s.vy1 : s.vy0) & (c >= 0) & (c < gm.C);
         if (valid) {
             const int64_t o = (int64_t)b * gm.sb + (int64_t)c * gm.sc + (int64_t)(s.y0 + (low ? 1 : 0)) * gm.sy +
                               (int64_t)(s.x0 + (right ? 1 : 0)) * gm.sx;

@@ -22,7 +22,7 @@ from . import _lib
 
 __all__ = [
     "ms_deform_attn_core", "sample_indices", "level_start_index", "locations_and_weights",
-    "pack_value", "clear_repack_cache", "set_default_coord_mode", "get_default_coord_mode",
+    "pack_value", "clear_repack_cache", "set_default_coord_mode", "get_default_coord_mode", "ValueList",
 ]
 
 _DTYPE_CODE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
@@ -80,45 +80,149 @@ def _require_cuda(t: torch.Tensor, name: str):
 # --------------------------------------------------------------------------
 # value layout: list of strided per-level views  ->  channel-last pyramid
 # --------------------------------------------------------------------------
-class _RepackCache:
-    """One-entry cache so that the decoder layers sharing one value list repack once.
+class ValueList:
+    """Lazy stand-in for the reference's value list (transformer.py:1285-1286) that remembers ``memory``.
 
-    Keyed on the identity of ``value[0]`` (held weakly) and the version counters of
-    every level, so a new forward pass -- new view objects, even at the same
-    address -- never hits a stale entry.
+    ``patch.install_value_producer`` makes ``Transformer.forward`` hand this to the decoder instead of the
+    permuted copy: the kernels read ``memory (N, S, C)`` directly (row f2: no repack, no un-repack), while
+    any other consumer that indexes / iterates it gets the reference's own per-level tensors, built on
+    first use by the reference's own expression.
     """
+
+    def __init__(self, memory: torch.Tensor, n_heads: int, split_sizes, dim=-1):
+        self.memory = memory
+        self.n_heads = int(n_heads)
+        self.split_sizes = [int(s) for s in split_sizes]
+        self._levels = None
+
+    def levels(self):
+        if self._levels is None:
+            v = self.memory.unflatten(2, (self.n_heads, -1)).permute(0, 2, 3, 1).flatten(0, 1)
+            self._levels = v.split(self.split_sizes, dim=-1)
+        return self._levels
+
+    def __len__(self):
+        return len(self.split_sizes)
+
+    def __getitem__(self, i):
+        return self.levels()[i]
+
+    def __iter__(self):
+        return iter(self.levels())
+
+
+class _ValueHub:
+    """State shared by every core call on one value (list) inside one autograd graph: the channel-last
+    pyramid (repacked once) and ONE fp32 gradient buffer that the backward launches of all decoder layers
+    accumulate into (C ABI ``accumulate=1``), handed to autograd -- and, for the reference's strided list,
+    un-repacked -- exactly once, by the token node's backward."""
+
+    __slots__ = ("pyramid", "shapes", "n_heads", "is_list", "value_meta", "buffer", "token", "tok_grad",
+                 "spent", "__weakref__")
+
+    def __init__(self, pyramid, shapes, n_heads, is_list, value_meta):
+        self.pyramid, self.shapes, self.n_heads = pyramid, shapes, n_heads
+        self.is_list, self.value_meta = is_list, value_meta
+        self.buffer = None
+        self.token = None
+        self.tok_grad = None
+        self.spent = False
+
+
+class _HubToken(torch.autograd.Function):
+    """1-element tensor that ties the core calls on one value to the value's autograd node."""
+
+    @staticmethod
+    def forward(ctx, hub, *value):
+        ctx.hub = hub
+        ctx.n = len(value)
+        return torch.zeros(1, dtype=torch.float32, device=value[0].device)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _):
+        hub = ctx.hub
+        gv, hub.buffer = hub.buffer, None
+        hub.spent = True                       # a later forward on the same value starts a new hub
+        if gv is None:
+            return (None,) * (1 + ctx.n)
+        if hub.is_list:
+            dtype = hub.value_meta[0][1]
+            grads = _unpack_grad(gv, hub.shapes, hub.n_heads, dtype if dtype in _DTYPE_CODE else torch.float32)
+            grads = [g.to(m[1]) for g, m in zip(grads, hub.value_meta)]
+        else:
+            shape, dtype = hub.value_meta[0]
+            grads = [gv.reshape(shape).to(dtype)]
+        stats["grad_handover"] += 1
+        return (None, *grads)
+
+
+class _HubCache:
+    """One-entry cache so that the decoder layers sharing one value (list) share one hub.
+
+    Keyed on the identity of the value object(s) (held weakly; the entry dies with them), their version
+    counters, the autograd mode and the CUDA stream, so a new forward pass -- new view objects, even at
+    the same address -- an in-place update, or a consumer on another stream never hits a stale entry."""
 
     def __init__(self):
         self._ref = None
         self._sig = None
-        self._pyramid = None
+        self._hub = None
 
-    def get(self, levels):
-        if self._ref is None or self._ref() is not levels[0]:
+    def get(self, tensors, grad):
+        if self._ref is None or self._ref() is not tensors[0]:
             return None
-        if self._sig != self._signature(levels):
+        if self._sig != self._signature(tensors, grad) or self._hub.spent:
             return None
-        return self._pyramid
+        return self._hub
 
-    def put(self, levels, pyramid):
-        self._ref = weakref.ref(levels[0])
-        self._sig = self._signature(levels)
-        self._pyramid = pyramid
+    def put(self, tensors, grad, hub):
+        me = weakref.ref(self)
+
+        def _gone(_):
+            c = me()
+            if c is not None and c._ref is not None and c._ref() is None:
+                c.clear()
+        self._ref = weakref.ref(tensors[0], _gone)
+        self._sig = self._signature(tensors, grad)
+        self._hub = hub
 
     def clear(self):
-        self._ref = self._sig = self._pyramid = None
+        self._ref = self._sig = self._hub = None
 
     @staticmethod
-    def _signature(levels):
-        return tuple((id(v), v._version, v.data_ptr(), tuple(v.shape), tuple(v.stride())) for v in levels)
+    def _signature(tensors, grad):
+        stream = torch.cuda.current_stream(tensors[0].device).cuda_stream if tensors[0].is_cuda else 0
+        return (grad, stream) + tuple((id(v), v._version, v.data_ptr(), tuple(v.shape), tuple(v.stride()))
+                                      for v in tensors)
 
 
-_repack_cache = _RepackCache()
-stats = {"repack_launches": 0, "forward_launches": 0, "backward_launches": 0}   # launch counters (tests, bench)
+_hub_cache = _HubCache()
+# launch counters (tests, bench)
+stats = {"repack_launches": 0, "forward_launches": 0, "backward_launches": 0, "grad_handover": 0,
+         "unpack_launches": 0}
 
 
 def clear_repack_cache() -> None:
-    _repack_cache.clear()
+    _hub_cache.clear()
+
+
+def _get_hub(value, shapes, n_heads) -> _ValueHub:
+    """Hub of ``value`` (a tensor, a ``ValueList`` or the reference's list of per-level tensors)."""
+    if isinstance(value, ValueList):
+        value = value.memory
+    is_list = not isinstance(value, torch.Tensor)
+    tensors = list(value) if is_list else [value]
+    grad = torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+    hub = _hub_cache.get(tensors, grad)
+    if hub is None:
+        pyramid = pack_value(tensors if is_list else value, shapes, n_heads)
+        hub = _ValueHub(pyramid, shapes, n_heads, is_list, [(tuple(v.shape), v.dtype) for v in tensors])
+        if grad:
+            hub.token = _HubToken.apply(hub, *tensors)
+            hub.tok_grad = torch.zeros(1, dtype=torch.float32, device=pyramid.device)
+        _hub_cache.put(tensors, grad, hub)
+    return hub
 
 
 def _zero_copy_view(levels, shapes, n_heads):
@@ -143,7 +247,7 @@ def _zero_copy_view(levels, shapes, n_heads):
     return torch.as_strided(v0, (n, acc, n_heads, dh), (n_heads * s_nh, s_s, s_nh, 1), v0.storage_offset())
 
 
-def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> torch.Tensor:
+def pack_value(value, spatial_shapes, n_heads: int) -> torch.Tensor:
     """Bring ``value`` into the kernel-native layout ``(N, S, H, Dh)`` (channel stride 1).
 
     Accepts the reference's list of ``(N*H, Dh, H_l*W_l)`` views (zero-copy when
@@ -153,6 +257,8 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
     """
     shapes = _shapes_tuple(spatial_shapes)
     total = sum(h * w for h, w in shapes)
+    if isinstance(value, ValueList):
+        value = value.memory
     if isinstance(value, torch.Tensor):
         _require_cuda(value, "value")
         if value.dtype == torch.float16:         # the reference's AMP is fp16 autocast: its sampler runs fp32
@@ -175,10 +281,6 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
     view = _zero_copy_view(levels, shapes, n_heads) if levels[0].dtype in _DTYPE_CODE else None
     if view is not None:
         return view
-    if use_cache:
-        hit = _repack_cache.get(levels)
-        if hit is not None:
-            return hit
     nh, dh, _ = levels[0].shape
     if nh % n_heads:
         raise ValueError(f"value leading dim {nh} is not a multiple of n_heads={n_heads}")
@@ -198,8 +300,6 @@ def pack_value(value, spatial_shapes, n_heads: int, use_cache: bool = True) -> t
             pyramid.data_ptr(), _code(dtype), n, n_heads, dh, len(shapes), _stream_ptr(pyramid.device))
     _lib.check(rc, "msda_b200_repack")
     stats["repack_launches"] += 1
-    if use_cache:
-        _repack_cache.put(list(value), pyramid)
     return pyramid
 
 
@@ -222,8 +322,12 @@ def _forward_raw(pyramid, shapes, loc, attn, out_dtype, coord_mode):
     return out
 
 
-def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, coord_mode, into=None):
-    """``into``: optional fp32 (N, S, H, Dh) buffer to ADD the value gradient to (layers sharing a value)."""
+def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, coord_mode, into=None,
+                  accumulate=None):
+    """``into``: optional fp32 (N, S, H, Dh) buffer for the value gradient; the launch ADDS to it
+    (``accumulate``, default when ``into`` is given: layers sharing a value) or overwrites it."""
+    if accumulate is None:
+        accumulate = into is not None
     n, total, n_heads, dh = pyramid.shape
     _, lq, _, n_levels, n_points, _ = loc.shape
     dev = pyramid.device
@@ -239,7 +343,7 @@ def _backward_raw(pyramid, shapes, loc, attn, grad_out, need_value, need_small, 
             pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
             _lib.i32_array([d for hw in shapes for d in hw]),
             loc.data_ptr(), attn.data_ptr(), grad_out.data_ptr(), _code(grad_out.dtype),
-            grad_value.data_ptr() if need_value else None, 1 if into is not None else 0,
+            grad_value.data_ptr() if need_value else None, 1 if (need_value and accumulate) else 0,
             grad_loc.data_ptr() if need_small else None,
             grad_attn.data_ptr() if need_small else None,
             n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(dev))
@@ -261,6 +365,7 @@ def _unpack_grad(grad_value, shapes, n_heads, dtype):
             _lib.i64_array([s for v in levels for s in v.stride()]),
             _code(dtype), n, n_heads, dh, len(shapes), _stream_ptr(buf.device))
     _lib.check(rc, "msda_b200_unpack_grad")
+    stats["unpack_launches"] += 1
     return levels
 
 
@@ -271,45 +376,46 @@ def _as_f32_contig(t: torch.Tensor) -> torch.Tensor:
 
 
 class _MSDACore(torch.autograd.Function):
-    """out = core(loc, attn, *value); value is one pyramid tensor or L per-level tensors."""
+    """out = core(loc, attn, token); the value pyramid and its shared gradient buffer live in the hub."""
 
     @staticmethod
-    def forward(ctx, loc, attn, meta, *value):
-        shapes, n_heads, coord_mode, out_dtype, is_list = meta
-        pyramid = pack_value(list(value) if is_list else value[0], shapes, n_heads)
+    def forward(ctx, loc, attn, meta, hub, token):
+        shapes, n_heads, coord_mode, out_dtype = meta
+        pyramid = hub.pyramid
         loc_c, attn_c = _as_f32_contig(loc), _as_f32_contig(attn)
         out = _forward_raw(pyramid, shapes, loc_c, attn_c, out_dtype or pyramid.dtype, coord_mode)
         ctx.meta = meta
-        ctx.pyramid = pyramid
-        ctx.value_meta = [(tuple(v.shape), v.dtype) for v in value]
+        ctx.hub = hub
         ctx.small_dtypes = (loc.dtype, attn.dtype)
-        ctx.save_for_backward(loc_c, attn_c)
+        # the pyramid goes through save_for_backward as well: an in-place change of value / memory between
+        # forward and backward then trips autograd's version check instead of giving silently wrong gradients
+        ctx.save_for_backward(loc_c, attn_c, pyramid)
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        shapes, n_heads, coord_mode, _, is_list = ctx.meta
-        loc_c, attn_c = ctx.saved_tensors
+        shapes, n_heads, coord_mode, _ = ctx.meta
+        loc_c, attn_c, pyramid = ctx.saved_tensors
+        hub = ctx.hub
         need_small = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        need_value = any(ctx.needs_input_grad[3:])
+        need_value = ctx.needs_input_grad[4]
         if grad_out.dtype not in _DTYPE_CODE:
             grad_out = grad_out.float()
         grad_out = grad_out.contiguous()
-        gv, gl, ga = _backward_raw(ctx.pyramid, shapes, loc_c, attn_c, grad_out, need_value, need_small,
-                                   coord_mode)
-        value_grads = [None] * len(ctx.value_meta)
+        into, first = hub.buffer, hub.buffer is None
+        if need_value and first:
+            n, total, _, dh = pyramid.shape
+            into = torch.empty((n, total, n_heads, dh), dtype=torch.float32, device=pyramid.device)
+        _, gl, ga = _backward_raw(pyramid, shapes, loc_c, attn_c, grad_out, need_value, need_small,
+                                  coord_mode, into=into if need_value else None, accumulate=not first)
+        tok = None
         if need_value:
-            if is_list:
-                dtype = ctx.value_meta[0][1]
-                value_grads = _unpack_grad(gv, shapes, n_heads, dtype if dtype in _DTYPE_CODE else torch.float32)
-                value_grads = [g.to(m[1]) for g, m in zip(value_grads, ctx.value_meta)]
-            else:
-                shape, dtype = ctx.value_meta[0]
-                value_grads = [gv.reshape(shape).to(dtype)]
+            hub.buffer = into
+            tok = hub.tok_grad                  # a non-None gradient, so that the token node runs
         if gl is not None:
             gl, ga = gl.to(ctx.small_dtypes[0]), ga.to(ctx.small_dtypes[1])
-        return (gl, ga, None, *value_grads)
+        return gl, ga, None, None, tok
 
 
 def ms_deform_attn_core(value, value_spatial_shapes, sampling_locations, attention_weights,
@@ -335,10 +441,9 @@ def ms_deform_attn_core(value, value_spatial_shapes, sampling_locations, attenti
         raise ValueError(f"{len(shapes)} spatial shapes for {n_levels} levels")
     if n_levels > _lib.MAX_LEVELS or n_points > _lib.MAX_POINTS:
         raise ValueError(f"at most {_lib.MAX_LEVELS} levels and {_lib.MAX_POINTS} points are supported")
-    is_list = not isinstance(value, torch.Tensor)
-    meta = (shapes, heads, _default_coord_mode if coord_mode is None else coord_mode, out_dtype, is_list)
-    args = tuple(value) if is_list else (value,)
-    return _MSDACore.apply(sampling_locations, attention_weights, meta, *args)
+    meta = (shapes, heads, _default_coord_mode if coord_mode is None else coord_mode, out_dtype)
+    hub = _get_hub(value, shapes, heads)
+    return _MSDACore.apply(sampling_locations, attention_weights, meta, hub, hub.token)
 
 
 def sample_indices(sampling_locations: torch.Tensor, spatial_shapes, coord_mode: int = None):

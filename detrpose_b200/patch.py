@@ -7,8 +7,9 @@ replacing that one global accelerates every ``MSDeformAttn`` instance while
 keeping the reference class -- its ``isinstance`` re-init hook
 (transformer.py:1154-1156), parameter names, ``state_dict`` and EMA copies -- exactly
 as it is.  Configurations outside the kernel contract (sampling modulation,
-region pooling, energy sampler) are routed, explicitly, to the reference's own
-function.  CPU tensors raise: this package has no CPU path (pass
+region pooling, energy sampler; more than 8 levels or 16 points, head widths that
+are not a multiple of 8 -- e.g. some grouped-offset / grid-attention set-ups) are
+routed, explicitly, to the reference's own function.  CPU tensors raise: this package has no CPU path (pass
 ``cpu_to_reference=True`` to hand them back to the reference's code instead,
 e.g. for ONNX export of a patched checkout).
 """
@@ -16,11 +17,33 @@ from __future__ import annotations
 
 import functools
 
+import torch
+
+from . import _lib
 from . import functional as MF
 
-__all__ = ["install", "uninstall", "make_core"]
+__all__ = ["install", "uninstall", "make_core", "install_value_producer", "uninstall_value_producer"]
 
 _ORIGINAL_ATTR = "_detrpose_b200_original_core"
+_ORIGINAL_ENCODER_INPUT = "_detrpose_b200_original_get_encoder_input"
+_VALUE_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
+
+
+def _inside_kernel_contract(value, sampling_locations) -> bool:
+    """Shapes / dtypes the kernels take (include/msda_b200.h): at most 8 levels and 16 points, head dim a
+    multiple of 8 up to 128, fp32 / bf16 (fp16 is up-cast) values.  Everything else is the reference's."""
+    if sampling_locations.dim() != 6:
+        return False
+    n_levels, n_points = sampling_locations.shape[3], sampling_locations.shape[4]
+    if n_levels > _lib.MAX_LEVELS or n_points > _lib.MAX_POINTS:
+        return False
+    if isinstance(value, MF.ValueList):
+        dh, dtype = value.memory.shape[-1] // value.n_heads, value.memory.dtype
+    elif isinstance(value, torch.Tensor):
+        dh, dtype = value.shape[-1] if value.dim() == 4 else value.shape[-1] // sampling_locations.shape[2], value.dtype
+    else:
+        dh, dtype = value[0].shape[1], value[0].dtype
+    return dh % 8 == 0 and 8 <= dh <= 128 and dtype in _VALUE_DTYPES
 
 
 def make_core(reference_core, cpu_to_reference: bool = False):
@@ -31,7 +54,8 @@ def make_core(reference_core, cpu_to_reference: bool = False):
              sampling_modulation=None, region_kernel_size=1, is_energy=False):
         baseline = (sampling_modulation is None and (region_kernel_size is None or region_kernel_size <= 1)
                     and not is_energy)
-        if not baseline or (cpu_to_reference and not sampling_locations.is_cuda):
+        if not baseline or (cpu_to_reference and not sampling_locations.is_cuda) \
+                or not _inside_kernel_contract(value, sampling_locations):
             return reference_core(value, value_spatial_shapes, sampling_locations, attention_weights,
                                   sampling_modulation=sampling_modulation,
                                   region_kernel_size=region_kernel_size, is_energy=is_energy)
@@ -54,3 +78,89 @@ def uninstall(reference_module) -> None:
     if original is not None:
         reference_module.ms_deform_attn_core_pytorch = original
         delattr(reference_module, _ORIGINAL_ATTR)
+
+
+# --------------------------------------------------------------------------
+# row f2: the value producer (transformer.py:1158-1177, 1285-1286)
+# --------------------------------------------------------------------------
+class _LazyHeads:
+    """What ``memory.unflatten(2, (nhead, -1))`` returns once the producer is patched: it follows the
+    reference's ``.permute(0, 2, 3, 1).flatten(0, 1).split(split_sizes, dim=-1)`` chain symbolically and
+    ends in a ``ValueList`` that still knows ``memory``; any other use gets the real tensor."""
+
+    def __init__(self, memory, sizes):
+        self._memory, self._sizes, self._stage = memory, sizes, 0
+
+    def _real(self):
+        t = self._memory.unflatten(2, self._sizes)
+        if self._stage >= 1:
+            t = t.permute(0, 2, 3, 1)
+        if self._stage >= 2:
+            t = t.flatten(0, 1)
+        return t
+
+    def permute(self, *dims):
+        dims = tuple(dims[0]) if len(dims) == 1 and not isinstance(dims[0], int) else dims
+        if self._stage == 0 and dims == (0, 2, 3, 1):
+            self._stage = 1
+            return self
+        return self._real().permute(*dims)
+
+    def flatten(self, start_dim=0, end_dim=-1):
+        if self._stage == 1 and (start_dim, end_dim) == (0, 1):
+            self._stage = 2
+            return self
+        return self._real().flatten(start_dim, end_dim)
+
+    def split(self, split_size, dim=0):
+        if self._stage == 2 and dim in (-1, 2) and not isinstance(split_size, int):
+            return MF.ValueList(self._memory, self._sizes[0], split_size)
+        return self._real().split(split_size, dim)
+
+    def __getattr__(self, name):
+        return getattr(self._real(), name)
+
+
+class _Memory(torch.Tensor):
+    """``memory`` as the patched producer returns it: a plain tensor for every op except ``unflatten``."""
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    def unflatten(self, dim, sizes):
+        plain = self.as_subclass(torch.Tensor)
+        sizes = tuple(sizes)
+        if dim == 2 and self.dim() == 3 and len(sizes) == 2 and sizes[1] == -1 and self.is_cuda \
+                and self.shape[2] % int(sizes[0]) == 0:
+            return _LazyHeads(plain, sizes)
+        return plain.unflatten(dim, sizes)
+
+
+def install_value_producer(reference_transformer_module) -> None:
+    """Let an UNMODIFIED ``Transformer.forward`` hand ``memory (N, S, C)`` itself to the kernels.
+
+    ``reference_transformer_module``: the imported ``src.models.detrpose.transformer`` module.  Its
+    ``Transformer._get_encoder_input`` (transformer.py:1158-1177) is wrapped so that the ``memory`` it returns
+    remembers its identity through the value construction at :1285-1286; the decoder then receives a
+    ``ValueList`` (same per-level tensors on demand, plus ``.memory``) instead of the permuted copy, the core
+    reads ``memory`` zero-copy, and all decoder layers add their value gradient into one fp32 channel-last
+    buffer that reaches autograd once."""
+    cls = reference_transformer_module.Transformer
+    if hasattr(cls, _ORIGINAL_ENCODER_INPUT):
+        return
+    original = cls._get_encoder_input
+
+    def _get_encoder_input(self, feats):
+        memory, spatial_shapes, split_sizes = original(self, feats)
+        if memory.is_cuda and type(memory) is torch.Tensor:
+            memory = memory.as_subclass(_Memory)
+        return memory, spatial_shapes, split_sizes
+
+    setattr(cls, _ORIGINAL_ENCODER_INPUT, original)
+    cls._get_encoder_input = _get_encoder_input
+
+
+def uninstall_value_producer(reference_transformer_module) -> None:
+    cls = reference_transformer_module.Transformer
+    original = getattr(cls, _ORIGINAL_ENCODER_INPUT, None)
+    if original is not None:
+        cls._get_encoder_input = original
+        delattr(cls, _ORIGINAL_ENCODER_INPUT)

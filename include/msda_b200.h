@@ -124,8 +124,9 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
  * grad_value      device fp32 (N, S, H, Dh) contiguous (may be NULL: skip)
  * accumulate      0: grad_value is OVERWRITTEN (every element written, the caller does not zero-fill);
  *                 1: the gradient is ADDED to the buffer (decoder layers sharing one `value`)
- * grad_locations  device fp32, shape of locations, overwritten (may be NULL together with grad_attention)
- * grad_attention  device fp32, shape of attention, overwritten
+ * grad_locations  device fp32, shape of locations, overwritten (may be NULL together with grad_attention);
+ *                 base pointer 32-BYTE aligned (written with 256-bit stores), else MSDA_ERR_ALIGN
+ * grad_attention  device fp32, shape of attention, overwritten; 16-byte aligned like every other buffer
  */
 MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_t* value_strides,
                        const int32_t* spatial_shapes,

@@ -121,3 +121,66 @@ def test_synthetic_inputs_are_seeded_and_shaped():
     assert a["locations"].min() >= -0.1 and a["locations"].max() <= 1.1
     d = synthetic.make_inputs(1, 4, 8, 16, w["shapes"], 6, seed=1, degenerate=True)
     assert torch.equal(d["locations"][..., 0, :], d["locations"][..., 5, :])
+
+
+# ---- row f2: value producer patch (host logic only, no kernels) ----
+def test_lazy_heads_follows_the_reference_chain_and_falls_back():
+    from detrpose_b200 import patch, functional as MF
+    mem = torch.randn(2, 10, 64, requires_grad=True)
+    sizes = [6, 4]
+    lazy = patch._LazyHeads(mem, (8, -1))
+    vl = lazy.permute(0, 2, 3, 1).flatten(0, 1).split(sizes, dim=-1)
+    assert isinstance(vl, MF.ValueList) and vl.memory is mem and vl.n_heads == 8 and len(vl) == 2
+    want = mem.unflatten(2, (8, -1)).permute(0, 2, 3, 1).flatten(0, 1).split(sizes, dim=-1)
+    assert all(torch.equal(a, b) for a, b in zip(vl, want))
+    assert torch.equal(vl[1], want[1])
+    # any other use of the intermediate gets the real tensor
+    other = patch._LazyHeads(mem, (8, -1)).permute(0, 1, 3, 2)
+    assert isinstance(other, torch.Tensor) and other.shape == (2, 10, 8, 8)
+    assert patch._LazyHeads(mem, (8, -1)).shape == (2, 10, 8, 8)
+    # gradients flow through the lazily built list like through the reference's expression
+    vl[0].sum().backward()
+    assert mem.grad is not None and float(mem.grad.abs().sum()) == 2 * 6 * 64
+
+
+def test_install_value_producer_wraps_and_restores():
+    import types
+    from detrpose_b200 import patch
+
+    class Transformer:
+        def _get_encoder_input(self, feats):
+            return feats[0], [[2, 5]], [10]
+
+    mod = types.SimpleNamespace(Transformer=Transformer)
+    original = Transformer._get_encoder_input
+    patch.install_value_producer(mod)
+    patch.install_value_producer(mod)                         # idempotent
+    assert Transformer._get_encoder_input is not original
+    mem = torch.randn(1, 10, 16)
+    out, shapes, sizes = Transformer()._get_encoder_input([mem])
+    assert type(out) is torch.Tensor and out is mem           # CPU tensors are left alone
+    patch.uninstall_value_producer(mod)
+    assert Transformer._get_encoder_input is original
+
+
+def test_memory_subclass_is_a_plain_tensor_for_everything_but_unflatten():
+    from detrpose_b200 import patch
+    mem = torch.randn(2, 10, 64, requires_grad=True)
+    m = (mem * 1).as_subclass(patch._Memory)
+    assert type(m.masked_fill(torch.zeros(2, 10, 1, dtype=torch.bool), 0.0)) is torch.Tensor
+    assert type(m + 1) is torch.Tensor and m.size(0) == 2 and m.requires_grad
+    v = m.unflatten(2, (8, -1))                               # CPU: the real op
+    assert type(v) is torch.Tensor and v.shape == (2, 10, 8, 8)
+    v.sum().backward()
+    assert mem.grad is not None
+
+
+def test_kernel_contract_routing_predicate():
+    from detrpose_b200 import patch
+    loc = torch.zeros(1, 3, 8, 2, 4, 2)
+    ok = [torch.zeros(8, 32, 6), torch.zeros(8, 32, 4)]
+    assert patch._inside_kernel_contract(ok, loc)
+    assert not patch._inside_kernel_contract([torch.zeros(8, 12, 6)], loc)            # Dh not a multiple of 8
+    assert not patch._inside_kernel_contract(ok, torch.zeros(1, 3, 8, 2, 20, 2))      # 20 points
+    assert not patch._inside_kernel_contract(ok, torch.zeros(1, 3, 8, 9, 4, 2))       # 9 levels
+    assert not patch._inside_kernel_contract([v.double() for v in ok], loc)
