@@ -195,13 +195,15 @@ def synthetic_targets(batch: int, device, seed: int = 0, max_persons: int = 8) -
 
 
 def install_kernels(*, core: bool = True, gate: bool = True, lqe: bool = True,
-                    value_producer: bool = True) -> None:
+                    value_producer: bool = True, fused_forward: bool = True) -> None:
     """Drop this package's kernels into the loaded reference modules (class / module-global patches, the
-    model objects themselves stay untouched): core (rows a1-a3), value hand-over (f2), Gate (f3), LQE (f4)."""
+    model objects themselves stay untouched): core (rows a1-a3), fused prologue (f1), value hand-over (f2), Gate (f3), LQE (f4)."""
     import detrpose_b200 as dp
     ref = load_reference()
     if core:
         dp.patch.install(ref.msda)
+    if fused_forward:
+        dp.patch.install_forward(ref.msda)
     if value_producer:
         dp.patch.install_value_producer(ref.transformer)
     if gate:
@@ -214,6 +216,7 @@ def uninstall_kernels() -> None:
     import detrpose_b200 as dp
     ref = load_reference()
     dp.patch.uninstall(ref.msda)
+    dp.patch.uninstall_forward(ref.msda)
     dp.patch.uninstall_value_producer(ref.transformer)
     dp.gate.uninstall_gate(ref.transformer)
     dp.lqe.uninstall_lqe(ref.transformer)

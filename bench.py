@@ -17,7 +17,14 @@ pinned HOST buffers, H2D + D2H inside the timed region; `roofline` = the dominan
 kernel against MEASURED_PEAKS.json; `cpu_baseline` = the reference's CPU op sequence
 (oracle/msda_torch.py) on a bounded sample, timed on this box's host cores.
 
-`--impl reference` times that CPU op sequence alone (all host threads), same metric/config.
+`--impl reference` times that CPU op sequence alone (all host threads), same metric/config (same 64 images).
+
+Further keys of the line: `reference_cuda` / `vs_reference_cuda` (the reference's own CUDA path -- per-level
+F.grid_sample + cat/mul/sum and its autograd backward -- on the same GPU, same 64 images: the kernel to
+beat), `e2e.copy_only_ms_per_step` (the same pinned-buffer traffic without any kernel: the host-side ceiling
+of the end-to-end number), `model_e2e` (baseline/model_bench.py: the unmodified reference DETRPose-S/L/X with
+the kernels dropped in, beside the same model on the reference's PyTorch path; under torchrun the training
+leg runs under DDP, so its curve over --gpus carries the NCCL gradient all-reduce).
 """
 from __future__ import annotations
 
@@ -39,7 +46,7 @@ METRIC = "msda_fwd_bwd_algorithmic_GBps"
 UNIT = "GB/s"
 WORKLOAD = "detrpose_s"
 BATCH_PER_GPU = 64
-CPU_SAMPLE_IMAGES = 16
+CPU_SAMPLE_IMAGES = 64          # the CPU arms run the GPU arm's batch (same_config)
 
 
 def parse_args():
@@ -56,6 +63,12 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU-local CPU cores")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-model", action="store_true", help="skip the whole-model legs (model_e2e)")
+    ap.add_argument("--no-refcuda", action="store_true", help="skip the reference-CUDA leg")
+    ap.add_argument("--quick-model", action="store_true", help="3 timed steps per whole-model leg")
+    ap.add_argument("--min-timed-ms", type=float, default=150.0,
+                    help="the K-step block is repeated until the timed region is at least this long; "
+                         "the median block is reported")
     ap.add_argument("--fwd-variant", type=int, default=-1)
     ap.add_argument("--bwd-variant", type=int, default=-1)
     return ap.parse_args()
@@ -188,6 +201,47 @@ def time_cpu_reference(w, dtype, images, steps, warmup):
     return gbps, total / len(times) * 1e3, torch.get_num_threads()
 
 
+def time_reference_cuda(w, inp, dev, stream, images, bytes_per_image):
+    """The reference's op sequence (oracle/msda_torch.core_fwd_bwd: per-level F.grid_sample + cat/mul/sum,
+    autograd backward -- ms_deform_attn.py:159-193) on the GPU, on the SAME images / locations / weights as
+    this arm, value handed over as the reference's own strided list (transformer.py:1285-1286):
+    fp32, and bf16 storage under torch.autocast (grid_sampler is on autocast's fp32 list: the sampler runs
+    fp32 on bf16-stored inputs, as with --amp)."""
+    from oracle import msda_torch as otorch          # the reference arm only
+    shapes = inp["shapes"]
+    loc, att = inp["locations"], inp["attention"]
+    arms = {}
+    for name, vdt in (("fp32", torch.float32), ("bf16_autocast", torch.bfloat16)):
+        mem = inp["memory"].to(vdt)
+        go = inp["grad_out"].to(vdt)
+        value = otorch.make_value_list(mem, w["H"], shapes)
+
+        def one():
+            if vdt == torch.bfloat16:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return otorch.core_fwd_bwd(value, shapes, loc, att, go.float())
+            return otorch.core_fwd_bwd(value, shapes, loc, att, go)
+
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.reset_peak_memory_stats(dev)
+        e0.record(stream)
+        for _ in range(5):
+            one()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / 5
+        arms[name] = {"ms_per_step": round(ms, 3), "GBps": round(images * bytes_per_image / (ms * 1e-3) / 1e9, 1),
+                      "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2)}
+        del value, mem, go
+        torch.cuda.empty_cache()
+    return {"arms": arms, "images": images,
+            "what": "reference op sequence on cuda (L x F.grid_sample + cat/mul/sum, autograd backward), value as "
+                    "the reference's strided list, same inputs as this arm; bytes counted with this arm's accounting"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -290,22 +344,32 @@ def run_b200_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warm_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(max(args.warmup, 3)):
+        if i == max(args.warmup, 3) - 1:
+            warm_ev[0].record(stream)
         step()
+    warm_ev[1].record(stream)
     barrier()
+    # The driver's K can be small (20 steps = 13 ms): the block of EXACTLY K steps is timed `blocks` times
+    # back to back (each block between its own pair of events) so that the whole timed region lasts at
+    # least --min-timed-ms and the clock sampler sees it; the median block is the reported one.
+    est_step_ms = shard.max_over_ranks(warm_ev[0].elapsed_time(warm_ev[1]), device=dev)
+    blocks = int(min(50, max(3, -(-args.min_timed_ms // max(est_step_ms * args.steps, 1e-3)))))
     per_step_events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    block_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(blocks)]
     barrier()
     sampler.mark_begin()
-    t_begin.record(stream)
-    for i in range(args.steps):
-        step(per_step_events[i])
-    t_end.record(stream)
+    for b in range(blocks):
+        block_ev[b][0].record(stream)
+        for i in range(args.steps):
+            step(per_step_events[i] if b == blocks - 1 else None)
+        block_ev[b][1].record(stream)
     barrier()
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = t_begin.elapsed_time(t_end)
-    elapsed_ms = shard.max_over_ranks(elapsed_ms, device=dev)
+    block_ms = sorted(shard.max_over_ranks(e0.elapsed_time(e1), device=dev) for e0, e1 in block_ev)
+    elapsed_ms = block_ms[len(block_ms) // 2]
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in per_step_events)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in per_step_events)
 
@@ -362,12 +426,29 @@ def run_b200_arm(args):
                     t.record_stream(s_out)
                 ev_done[b].record(s_out)
 
-        def e2e_run(steps):
+        # copy-only twin: the same pinned buffers, streams, events and bytes, no kernel -- what the host side
+        # of the box (PCIe, pinned-page DMA behind one NUMA node) allows at this number of ranks
+        dummy = {"o": torch.empty_like(out), "gm": torch.empty_like(inp["memory"]),
+                 "gl": torch.empty_like(loc), "ga": torch.empty_like(att)}
+
+        def copy_and_download(b):
+            stream.wait_event(ev_in[b])
+            ev_comp[b].record(stream)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_comp[b])
+                h_out.copy_(dummy["o"], non_blocking=True)
+                h_gm.copy_(dummy["gm"], non_blocking=True)
+                h_gl.copy_(dummy["gl"], non_blocking=True)
+                h_ga.copy_(dummy["ga"], non_blocking=True)
+                ev_done[b].record(s_out)
+
+        def e2e_run(steps, body=None):
+            body = body or compute_and_download
             upload(0)
             for i in range(steps):
                 if i + 1 < steps:
                     upload((i + 1) & 1)
-                compute_and_download(i & 1)
+                body(i & 1)
             stream.wait_stream(s_out)
 
         e2e_steps = max(4, min(args.steps, 12))
@@ -387,11 +468,27 @@ def run_b200_arm(args):
             barrier()
             repeats.append(shard.max_over_ranks(e0.elapsed_time(e1), device=dev))
         e2e_ms = sorted(repeats)[len(repeats) // 2]
+        copy_repeats = []
+        e2e_run(e2e_steps, copy_and_download)
+        for _ in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            s_in.wait_event(e0)
+            e2e_run(e2e_steps, copy_and_download)
+            e1.record(stream)
+            barrier()
+            copy_repeats.append(shard.max_over_ranks(e0.elapsed_time(e1), device=dev))
+        copy_ms = sorted(copy_repeats)[1]
         e2e_bytes = shard.job_total(N * (b_f + b_b) * e2e_steps, device=dev)
         e2e = {"value": round(e2e_bytes / (e2e_ms * 1e-3) / 1e9, 3), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                "ms_per_step": round(e2e_ms / e2e_steps, 3),
                "repeats_ms_per_step": [round(r / e2e_steps, 3) for r in repeats], "reported": "median of 5 repeats",
+               "copy_only_ms_per_step": round(copy_ms / e2e_steps, 3),
+               "frac_of_copy_only": round(copy_ms / e2e_ms, 3),
+               "copy_only_note": "same pinned buffers / streams / bytes with no kernel launched (median of 3): "
+                                 "the ceiling the host side of this box sets for e2e at this rank count",
                "cpu_affinity": affinity,
                "api": "detrpose_b200.ms_deform_attn_core + torch.autograd.grad; pinned host buffers, "
                       "upload / compute / download on separate streams, double-buffered"}
@@ -404,7 +501,7 @@ def run_b200_arm(args):
         vlist = list(inp["memory"].unflatten(2, (w["H"], -1)).permute(0, 2, 3, 1).flatten(0, 1).split(sizes, dim=-1))
 
         def ref_step():
-            pyr = MF.pack_value(vlist, shapes, w["H"], use_cache=False)
+            pyr = MF.pack_value(vlist, shapes, w["H"])
             o = MF._forward_raw(pyr, shapes, loc, att, vdt, cm)
             gv, gl, ga = MF._backward_raw(pyr, shapes, loc, att, go, True, True, cm)
             return o, MF._unpack_grad(gv, shapes, w["H"], vdt), gl, ga
@@ -424,12 +521,38 @@ def run_b200_arm(args):
                               "gradient un-repack per step; in the model they amortise over the 3-6 decoder layers "
                               "that share the list"}
 
+    # ---- the kernel to beat: the reference's own CUDA path on this GPU, same images (rank 0) ----
+    ref_cuda = None
+    if rank == 0 and not args.no_refcuda:
+        try:
+            ref_cuda = time_reference_cuda(w, inp, dev, stream, N, b_f + b_b)
+            ours_ms = elapsed_ms / args.steps
+            ref_cuda["vs_reference_cuda"] = {
+                "this_arm_zero_copy_vs_" + k: round(v["ms_per_step"] / ours_ms, 2)
+                for k, v in ref_cuda["arms"].items()}
+            if ref_layout is not None:
+                ref_cuda["vs_reference_cuda"].update({
+                    "this_arm_list_interface_vs_" + k: round(v["ms_per_step"] / ref_layout["ms_per_step"], 2)
+                    for k, v in ref_cuda["arms"].items()})
+        except Exception as e:                                   # noqa: BLE001 -- reported in the line
+            ref_cuda = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- whole-model legs (every rank takes part: the training leg runs under DDP) ----
+    model_e2e = None
+    if not args.no_model and args.workload == WORKLOAD:
+        del grad_value, grad_loc, grad_att, out
+        torch.cuda.empty_cache()
+        lib.msda_b200_set_variant(-1, -1)
+        from baseline import model_bench
+        model_e2e = model_bench.run(dev, world, quick=args.quick_model)
+
     # ---- CPU baseline (rank 0, N=1 only): the reference's CPU op sequence on a bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        gbps, ms, threads = time_cpu_reference(w, args.dtype, CPU_SAMPLE_IMAGES, steps=12, warmup=2)
+        gbps, ms, threads = time_cpu_reference(w, args.dtype, CPU_SAMPLE_IMAGES, steps=6, warmup=1)
         cpu = {"value": round(gbps, 4), "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload x 12 timed fwd+bwd passes "
+               "sample": f"{CPU_SAMPLE_IMAGES} images of the same workload (the GPU arm's batch) x 6 timed fwd+bwd passes "
                          f"({ms:.0f} ms each), fp32 on CPU via oracle/msda_torch.py (the reference's op sequence); "
                          f"bytes counted with the {args.dtype} accounting of the GPU arm"}
 
@@ -439,6 +562,8 @@ def run_b200_arm(args):
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed_ms / args.steps, 4),
+            "timed_blocks": {"blocks_of_K_steps": blocks, "reported": "median block",
+                             "block_ms": [round(b, 3) for b in block_ms]},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": config_dict(args, w, images=N),
@@ -451,9 +576,12 @@ def run_b200_arm(args):
                          "unit": "GB/s", "frac": round(bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak, 4),
                          "peak_source": peak_src,
                          "traffic": traffic.get("backward_dram_bytes_per_launch") if traffic else None,
+                         "traffic_source": (traffic.get("source") if traffic else None) or
+                                           "committed ncu --set full capture (profiles/traffic.json), not re-measured in this run",
                          "algorithmic_bytes_per_launch": int(bwd_bytes)},
             "reference_value_list_layout": ref_layout,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+            "reference_cuda": ref_cuda, "model_e2e": model_e2e,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 2 * args.steps * blocks, "clocks": clocks,
         }
         sys.stdout.write(json.dumps(line) + "\n")
         sys.stdout.flush()

@@ -35,6 +35,14 @@ SIGNATURES = {
     "msda_b200_backward": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,
                                    c_void_p, c_int, c_void_p, c_void_p,
                                    c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msda_b200_fused_supported": (c_int, [c_int, _I64P, _I32P, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "msda_b200_forward_fused": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_int, c_void_p,
+                                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msda_b200_backward_fused": (c_int, [c_void_p, c_int, _I64P, _I32P, c_void_p, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "msda_b200_softmax_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "msda_b200_sample_indices": (c_int, [_I32P, c_void_p, c_void_p, c_void_p,
                                          c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "msda_b200_locations": (c_int, [c_void_p, c_void_p, c_void_p, c_int, _I32P, c_void_p, c_void_p,

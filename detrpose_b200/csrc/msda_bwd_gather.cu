@@ -134,13 +134,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ONE: the whole query range fits one chunk and grad_value is overwritten -- the common case; the
 // read-modify-write paths and the chunk bookkeeping compile away (less register pressure).
-template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE>
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, int MODE = 0>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float* __restrict__ loc,
                   const float* __restrict__ attn, const char* __restrict__ grad_out,
                   float* __restrict__ grad_value, float* __restrict__ grad_loc,
                   float* __restrict__ grad_attn, const int accumulate, const int q_chunk,
-                  const int bins_words_max) {
+                  const int bins_words_max, const float* __restrict__ ref, const int ref_levels) {
     constexpr int E = Vec<VBF>::kElems;
     constexpr int E2 = E / 2;
     constexpr int ES = VBF ? 2 : 4;
@@ -212,6 +212,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const int npix = Hl * Wl;
     const float inv_w = 1.0f / (float)Wl;
     const float fW = (float)Wl, fH = (float)Hl;
+    const float sW = ref != nullptr ? 1.0f : fW, sH = ref != nullptr ? 1.0f : fH;
     // (q, p) of sample tid and the step to sample tid + THREADS
     const int q_t0 = tid / P, p_t0 = tid - q_t0 * P;
     const int dq = THREADS / P, dp = THREADS - dq * P;
@@ -281,8 +282,15 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         {
             int q = q_t0, p = p_t0;
             for (int i = tid; i < nsamp; i += THREADS) {
-                const float2 xy = loc_s[i];
+                float2 xy = loc_s[i];
                 const float a = att_s[i];
+                if (ref != nullptr) {
+                    // fused prologue (row f1): the staged pairs are sampling offsets; location = ref + offset /
+                    // (W_l, H_l) with the divide and the add rounded separately (ms_deform_attn.py:414-416)
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(ref) +
+                                           ((int64_t)n * pb.Lq + q0 + q) * ref_levels + (ref_levels == 1 ? 0 : l));
+                    xy = make_float2(__fadd_rn(r.x, __fdiv_rn(xy.x, fW)), __fadd_rn(r.y, __fdiv_rn(xy.y, fH)));
+                }
                 const Sample s = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
                 const bool inside = s.x0 >= -1 && s.x0 < Wl && s.y0 >= -1 && s.y0 < Hl;
                 float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);     // unbinned: .w == 0
@@ -455,6 +463,38 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             ga_m = ((id >> 16) & 0xfffu) * (VPR * 16);
                         }
                         float d[4];
+                        if constexpr (MODE == 1) {
+                            // software-pipelined batch: the 8 broadcasts and the 4 g-row loads of the batch are
+                            // issued before the first FMA (idle slots read the zero row with weight zero), so a
+                            // warp exposes one shuffle + one shared-load latency per batch instead of per visit
+                            float w4[4];
+                            uint32_t ga4[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                w4[u] = __shfl_sync(FULL, w_m, u, 4);
+                                ga4[u] = __shfl_sync(FULL, ga_m, u, 4);
+                            }
+                            uint4 graw[4][K];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                                for (int k = 0; k < K; ++k) graw[u][k] = lds_u4(a_g + ga4[u] + k * G * 16);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float2 d2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    float2 g[E2];
+                                    unpack2<VBF>(graw[u][k], g);
+#pragma unroll
+                                    for (int c = 0; c < E2; ++c) {
+                                        if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
+                                        acc[k * E2 + c] = fma2(g[c], make_float2(w4[u], w4[u]), acc[k * E2 + c]);
+                                    }
+                                }
+                                d[u] = d2.x + d2.y;
+                            }
+                        } else {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             d[u] = 0.0f;
@@ -474,6 +514,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                                 }
                                 d[u] = d2.x + d2.y;
                             }
+                        }
                         }
                         if (SMALL) {
                             const bool hi2 = lane & 2, hi1 = lane & 1;
@@ -660,7 +701,9 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 const float ga = wx0 * wy0 * d0 + wx1 * wy0 * d1 + wx0 * wy1 * d2 + wx1 * wy1 * d3;
                 const float gx = (d1 - d0) * wy0 + (d3 - d2) * wy1;
                 const float gy = (d2 - d0) * wx0 + (d3 - d1) * wx1;
-                *reinterpret_cast<float4*>(dots_s + slot * 4) = make_float4(ga, a * fW * gx, a * fH * gy, 0.0f);
+                // d(pixel coordinate)/d(location) = (W_l, H_l); with the fused prologue the gradient is taken
+                // w.r.t. the offsets, location = ref + offset / (W_l, H_l), and the factors cancel
+                *reinterpret_cast<float4*>(dots_s + slot * 4) = make_float4(ga, a * sW * gx, a * sH * gy, 0.0f);
             }
             __syncthreads();
             if (pbuf != nullptr && tid == 0 && chunk == 0) pbuf[(size_t)blockIdx.x * 8 + 7] = (unsigned long long)l;
@@ -695,11 +738,16 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
 #undef MSDA_STAMP
 }
 
-template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE>
+// reference points of the fused-prologue call in flight on this thread (set by backward_gather around the
+// dispatch below; the dispatch macros stay as they are)
+static thread_local const float* g_fused_ref = nullptr;
+static thread_local int g_fused_ref_levels = 1;
+
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, int MODE = 0>
 static cudaError_t launch_gather_impl(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
                                       const float* attn, const void* go, float* gv, float* gl, float* ga,
-                                      int accumulate, cudaStream_t st) {
-    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL, ONE>;
+                                      int accumulate, cudaStream_t st, const float* ref, int ref_levels) {
+    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL, ONE, MODE>;
     static thread_local int configured_for = -1;      // per-thread cache of the attribute call (per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -710,19 +758,21 @@ static cudaError_t launch_gather_impl(const Problem& pb, const GatherPlan& plan,
     }
     const unsigned grid = (unsigned)(pb.N * pb.H * pb.L);
     kern<<<grid, THREADS, plan.smem_bytes, st>>>(pb, (const char*)value, loc, attn, (const char*)go, gv, gl, ga,
-                                                  accumulate, plan.q_chunk, plan.bins_words);
+                                                  accumulate, plan.q_chunk, plan.bins_words, ref, ref_levels);
     return cudaGetLastError();
 }
 
-template <int G, int K, bool VBF, int THREADS>
+template <int G, int K, bool VBF, int THREADS, int MODE = 0>
 static cudaError_t launch_gather(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
                                  const float* attn, const void* go, float* gv, float* gl, float* ga,
                                  int accumulate, cudaStream_t st) {
     const bool one = plan.n_chunks == 1 && !accumulate;
+    const float* ref = g_fused_ref;
+    const int rl = g_fused_ref_levels;
     if (gl != nullptr)
-        return one ? launch_gather_impl<G, K, VBF, THREADS, true, true>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st)
-                   : launch_gather_impl<G, K, VBF, THREADS, true, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
-    return launch_gather_impl<G, K, VBF, THREADS, false, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
+        return one ? launch_gather_impl<G, K, VBF, THREADS, true, true, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl)
+                   : launch_gather_impl<G, K, VBF, THREADS, true, false, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
+    return launch_gather_impl<G, K, VBF, THREADS, false, false, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
 }
 
 // Returns false when the shape does not fit the gather kernel (caller falls back to the flat one).
@@ -755,13 +805,44 @@ bool backward_gather_supported(const Problem& pb, bool value_bf16) {
     return make_plan(pb, pb.Dh * (value_bf16 ? 2 : 4), plan);
 }
 
+static cudaError_t backward_gather_dispatch(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                                            const float* attn, const void* grad_out, float* grad_value,
+                                            float* grad_loc, float* grad_attn, int accumulate, int threads_pref,
+                                            cudaStream_t st);
+
 cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                             const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
-                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st) {
+                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st,
+                            const float* ref, int ref_levels) {
+    g_fused_ref = ref;
+    g_fused_ref_levels = ref_levels;
+    const cudaError_t e = backward_gather_dispatch(pb, value, value_bf16, loc, attn, grad_out, grad_value, grad_loc,
+                                                   grad_attn, accumulate, threads_pref, st);
+    g_fused_ref = nullptr;
+    return e;
+}
+
+static cudaError_t backward_gather_dispatch(const Problem& pb, const void* value, bool value_bf16, const float* loc,
+                                            const float* attn, const void* grad_out, float* grad_value,
+                                            float* grad_loc, float* grad_attn, int accumulate, int threads_pref,
+                                            cudaStream_t st) {
     GatherPlan plan;
     if (!make_plan(pb, pb.Dh * (value_bf16 ? 2 : 4), plan)) return cudaErrorInvalidValue;
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
     const bool wide_regs = threads_pref == 512;
+    // experimental instantiations (bf16, Dh = 32 only), selected through msda_b200_set_variant(_, 10..14)
+    if (threads_pref >= 10 && threads_pref <= 14 && nv == 4 && value_bf16) {
+#define MSDA_X(G_, K_, T_, M_) return launch_gather<G_, K_, true, T_, M_>(pb, plan, value, loc, attn, grad_out, \
+                                                                       grad_value, grad_loc, grad_attn, accumulate, st)
+        switch (threads_pref) {
+            case 10: MSDA_X(2, 2, 512, 0);
+            case 11: MSDA_X(2, 2, 768, 0);
+            case 12: MSDA_X(4, 1, 1024, 1);
+            case 13: MSDA_X(4, 1, 768, 1);
+            case 14: MSDA_X(4, 1, 512, 1);
+        }
+#undef MSDA_X
+    }
     if (threads_pref == 768 && nv == 4)          // 768 threads x 85 registers
         return value_bf16 ? launch_gather<4, 1, true, 768>(pb, plan, value, loc, attn, grad_out, grad_value,
                                                            grad_loc, grad_attn, accumulate, st)
@@ -800,6 +881,55 @@ cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf1
         default: return cudaErrorInvalidValue;
     }
 #undef MSDA_GATHER_CASE
+}
+
+// ---------------------------------------------------------------------------
+// Softmax backward of the fused prologue: grad_logits = a * (g - sum_j a_j g_j) over the L*P weights of one
+// (n, q, h) (ms_deform_attn.py:393).  The sum spans all levels, i.e. several CTAs of the gather kernel, so
+// it is a pass of its own: one thread per row, rows are consecutive 16-byte-aligned runs of `cols` floats.
+// ---------------------------------------------------------------------------
+template <int COLS>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ attn, const float* __restrict__ grad_attn,
+                   float* __restrict__ grad_logits, const int64_t rows, const int cols_rt) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int cols = COLS > 0 ? COLS : cols_rt;
+    const float* a = attn + r * cols;
+    const float* g = grad_attn + r * cols;
+    float* o = grad_logits + r * cols;
+    if constexpr (COLS > 0 && COLS % 4 == 0) {
+        float4 av[COLS / 4], gv[COLS / 4];
+#pragma unroll
+        for (int i = 0; i < COLS / 4; ++i) {
+            av[i] = __ldg(reinterpret_cast<const float4*>(a) + i);
+            gv[i] = __ldg(reinterpret_cast<const float4*>(g) + i);
+        }
+        float dot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < COLS / 4; ++i)
+            dot += av[i].x * gv[i].x + av[i].y * gv[i].y + av[i].z * gv[i].z + av[i].w * gv[i].w;
+#pragma unroll
+        for (int i = 0; i < COLS / 4; ++i)
+            reinterpret_cast<float4*>(o)[i] = make_float4(av[i].x * (gv[i].x - dot), av[i].y * (gv[i].y - dot),
+                                                          av[i].z * (gv[i].z - dot), av[i].w * (gv[i].w - dot));
+    } else {
+        float dot = 0.0f;
+        for (int i = 0; i < cols; ++i) dot += __ldg(a + i) * __ldg(g + i);
+        for (int i = 0; i < cols; ++i) o[i] = __ldg(a + i) * (__ldg(g + i) - dot);
+    }
+}
+
+cudaError_t softmax_backward(const float* attn, const float* grad_attn, float* grad_logits, int64_t rows,
+                             int cols, cudaStream_t st) {
+    const unsigned grid = (unsigned)((rows + 255) / 256);
+    switch (cols) {
+        case 8: softmax_bwd_kernel<8><<<grid, 256, 0, st>>>(attn, grad_attn, grad_logits, rows, cols); break;
+        case 12: softmax_bwd_kernel<12><<<grid, 256, 0, st>>>(attn, grad_attn, grad_logits, rows, cols); break;
+        case 16: softmax_bwd_kernel<16><<<grid, 256, 0, st>>>(attn, grad_attn, grad_logits, rows, cols); break;
+        default: softmax_bwd_kernel<0><<<grid, 256, 0, st>>>(attn, grad_attn, grad_logits, rows, cols); break;
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace msda

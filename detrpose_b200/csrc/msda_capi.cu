@@ -182,12 +182,13 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
     // registers); variant 0: flat + vector reductions
     const int variant = g_bwd_variant.load();
     const bool can_gather = grad_out_dtype == value_dtype && msda::backward_gather_supported(pb, vbf);
-    if ((variant == 1 || variant == 2 || variant == 3) && !can_gather)
+    if ((variant == 1 || variant == 2 || variant == 3 || variant >= 10) && !can_gather)
         return fail(MSDA_ERR_SHAPE, "gather-form backward does not support this shape/dtype combination");
     cudaError_t e;
     if (can_gather && variant != 0) {
         e = msda::backward_gather(pb, value, vbf, locations, attention, grad_out, grad_value, grad_locations,
-                                  grad_attention, accumulate, variant == 2 ? 512 : variant == 3 ? 768 : 1024, st);
+                                  grad_attention, accumulate,
+                                  variant >= 10 ? variant : variant == 2 ? 512 : variant == 3 ? 768 : 1024, st);
     } else {
         if (grad_value && !accumulate) {
             e = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * pb.S * H * Dh, st);
@@ -197,6 +198,85 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
                                 grad_value, grad_locations, grad_attention, st);
     }
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_backward launch");
+}
+
+// ---- fused prologue (row f1) ----
+static bool fused_ok(const msda::Problem& pb, bool vbf) {
+    return msda::forward_lean_supported(pb, vbf) && msda::backward_gather_supported(pb, vbf);
+}
+
+MSDA_API int msda_b200_fused_supported(int value_dtype, const int64_t* value_strides, const int32_t* spatial_shapes,
+                              int N, int Lq, int H, int Dh, int L, int P) {
+    msda::Problem pb;
+    if (make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, MSDA_COORD_FMA)) return 0;
+    if (value_dtype != MSDA_F32 && value_dtype != MSDA_BF16) return 0;
+    if (value_strides) { pb.vs_n = value_strides[0]; pb.vs_s = value_strides[1]; pb.vs_h = value_strides[2]; }
+    return fused_ok(pb, value_dtype == MSDA_BF16) ? 1 : 0;
+}
+
+MSDA_API int msda_b200_forward_fused(const void* value, int value_dtype, const int64_t* value_strides,
+                            const int32_t* spatial_shapes, const float* offsets, const float* logits,
+                            const float* ref_points, int ref_levels, void* out, int out_dtype,
+                            float* attention_out, int N, int Lq, int H, int Dh, int L, int P,
+                            int coord_mode, void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, coord_mode);
+    if (rc) return rc;
+    if ((rc = set_value_strides(pb, value, value_dtype, value_strides))) return rc;
+    if (!offsets || !logits || !ref_points || !out) return fail(MSDA_ERR_NULL, "offsets / logits / ref_points / out is NULL");
+    if (ref_levels != 1 && ref_levels != L) return fail(MSDA_ERR_SHAPE, "ref_levels=%d must be 1 or L=%d", ref_levels, L);
+    if (out_dtype != MSDA_F32 && out_dtype != MSDA_BF16) return fail(MSDA_ERR_DTYPE, "unknown out dtype %d", out_dtype);
+    if (!aligned16(out) || !aligned16(offsets) || !aligned16(logits) || (attention_out && !aligned16(attention_out)) ||
+        (reinterpret_cast<uintptr_t>(ref_points) & 7u))
+        return fail(MSDA_ERR_ALIGN, "fused forward: offsets / logits / out / attention_out must be 16-byte, ref_points 8-byte aligned");
+    const bool vbf = value_dtype == MSDA_BF16;
+    if (!msda::forward_lean_supported(pb, vbf)) return fail(MSDA_ERR_SHAPE, "fused forward does not support this shape");
+    const cudaError_t e = msda::forward_lean(pb, value, vbf, offsets, logits, out, out_dtype == MSDA_BF16, 4,
+                                             (cudaStream_t)stream, ref_points, ref_levels, attention_out);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward_fused launch");
+}
+
+MSDA_API int msda_b200_backward_fused(const void* value, int value_dtype, const int64_t* value_strides,
+                             const int32_t* spatial_shapes, const float* offsets, const float* ref_points,
+                             int ref_levels, const float* attention, const void* grad_out, int grad_out_dtype,
+                             float* grad_value, int accumulate, float* grad_offsets, float* grad_attention,
+                             int N, int Lq, int H, int Dh, int L, int P, int coord_mode, void* stream) {
+    msda::Problem pb;
+    int rc = make_problem(pb, N, Lq, H, Dh, L, P, spatial_shapes, coord_mode);
+    if (rc) return rc;
+    if ((rc = set_value_strides(pb, value, value_dtype, value_strides))) return rc;
+    if (!offsets || !ref_points || !attention || !grad_out)
+        return fail(MSDA_ERR_NULL, "offsets / ref_points / attention / grad_out is NULL");
+    if (ref_levels != 1 && ref_levels != L) return fail(MSDA_ERR_SHAPE, "ref_levels=%d must be 1 or L=%d", ref_levels, L);
+    if ((grad_offsets == nullptr) != (grad_attention == nullptr))
+        return fail(MSDA_ERR_NULL, "grad_offsets and grad_attention must be given together");
+    if (grad_out_dtype != value_dtype)
+        return fail(MSDA_ERR_DTYPE, "fused backward: grad_out dtype %d must equal the value dtype %d", grad_out_dtype, value_dtype);
+    if (!aligned16(grad_out) || !aligned16(offsets) || !aligned16(attention) || (grad_value && !aligned16(grad_value)) ||
+        (grad_attention && !aligned16(grad_attention)) || (reinterpret_cast<uintptr_t>(ref_points) & 7u))
+        return fail(MSDA_ERR_ALIGN, "fused backward buffers must be 16-byte aligned (ref_points 8-byte)");
+    if (grad_offsets && (reinterpret_cast<uintptr_t>(grad_offsets) & 31u))
+        return fail(MSDA_ERR_ALIGN, "grad_offsets must be 32-byte aligned");
+    if (!grad_value && !grad_offsets) return MSDA_OK;
+    const bool vbf = value_dtype == MSDA_BF16;
+    if (!msda::backward_gather_supported(pb, vbf)) return fail(MSDA_ERR_SHAPE, "fused backward does not support this shape");
+    const int variant = g_bwd_variant.load();
+    const cudaError_t e = msda::backward_gather(pb, value, vbf, offsets, attention, grad_out, grad_value, grad_offsets,
+                                                grad_attention, accumulate,
+                                                variant >= 10 ? variant : variant == 2 ? 512 : variant == 3 ? 768 : 1024,
+                                                (cudaStream_t)stream, ref_points, ref_levels);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_backward_fused launch");
+}
+
+MSDA_API int msda_b200_softmax_backward(const float* attention, const float* grad_attention, float* grad_logits,
+                               int64_t rows, int cols, void* stream) {
+    if (!attention || !grad_attention || !grad_logits) return fail(MSDA_ERR_NULL, "softmax backward: NULL argument");
+    if (rows <= 0 || cols <= 0 || cols > MSDA_MAX_LEVELS * MSDA_MAX_POINTS)
+        return fail(MSDA_ERR_SHAPE, "softmax backward: rows=%lld cols=%d", (long long)rows, cols);
+    if (!aligned16(attention) || !aligned16(grad_attention) || !aligned16(grad_logits))
+        return fail(MSDA_ERR_ALIGN, "softmax backward: buffers must be 16-byte aligned");
+    const cudaError_t e = msda::softmax_backward(attention, grad_attention, grad_logits, rows, cols, (cudaStream_t)stream);
+    return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_softmax_backward launch");
 }
 
 MSDA_API int msda_b200_sample_indices(const int32_t* spatial_shapes, const float* locations, int32_t* idx_out,

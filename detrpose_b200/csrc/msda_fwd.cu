@@ -125,11 +125,23 @@ struct __align__(16) SampleParams {
     uint32_t off[4];     // byte offset of the (clamped) corner row from the (n, h) base; off[0] == ~0u: no valid corner
 };
 
+// Fused prologue: with fz.ref != nullptr the kernel takes the raw Linear outputs
+// instead of locations / attention -- `loc` points at the sampling offsets (N, Lq, H, L, P, 2), `attn` at the
+// attention logits (N, Lq, H, L*P) -- and does ms_deform_attn.py:392-393 (softmax over L*P) and :412-416
+// (ref + offsets / (W_l, H_l), divide and add separately rounded) in phase 1, with the arithmetic of
+// `locations_kernel`, so locations and weights are bit-identical to the two-kernel path and never touch HBM.
+// attn_out (optional) keeps the softmaxed weights for the backward.
+struct FusedPrologue {
+    const float* ref;       // (N, Lq, ref_levels, 2) reference points; nullptr: not fused
+    int ref_levels;         // 1 or L
+    float* attn_out;        // (N, Lq, H, L, P) or nullptr
+};
+
 template <int G, int K, bool VBF, bool OBF, int MINB>
 __global__ void __launch_bounds__(kFwdThreads, MINB)
 fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 const float* __restrict__ loc, const float* __restrict__ attn,
-                char* __restrict__ out) {
+                char* __restrict__ out, const FusedPrologue fz) {
     constexpr int E = Vec<VBF>::kElems;
     constexpr int E2 = E / 2;
     constexpr int ES = VBF ? 2 : 4;
@@ -147,6 +159,20 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     // An item's parameters take LP*32 + 16 bytes: the 16-byte pad staggers the items of a warp
     // over the banks (LP*32 alone is a multiple of 128 for the model shapes: 8-way conflicts).
     const int item_stride = LP * 32 + 16;
+    const bool fused = fz.ref != nullptr;
+    float2* stat_s = reinterpret_cast<float2*>(smem_raw + IPC * item_stride);     // {max, sum} per item (fused)
+    if (fused) {
+        // softmax statistics, one thread per item (same loops as locations_kernel: same rounding)
+        if (tid < nitems) {
+            const float* lg = attn + (item0 + tid) * LP;
+            float m = -INFINITY;
+            for (int i = 0; i < LP; ++i) m = fmaxf(m, __ldg(lg + i));
+            float sum = 0.0f;
+            for (int i = 0; i < LP; ++i) sum += expf(__ldg(lg + i) - m);
+            stat_s[tid] = make_float2(m, sum);
+        }
+        __syncthreads();
+    }
     {
         const int nsamp = nitems * LP;
         const float2* lsrc = reinterpret_cast<const float2*>(loc) + item0 * LP;
@@ -168,10 +194,19 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
 #pragma unroll
             for (int u = 0; u < PF; ++u) {
                 if (s0 + u * kFwdThreads >= nsamp) break;
-                const float2 xy = xy_[u];
-                const float a = a_[u];
+                float2 xy = xy_[u];
+                float a = a_[u];
                 const int l = sl / pb.P;
                 const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
+                if (fused) {
+                    const float2 st = stat_s[il];
+                    a = expf(a - st.x) / st.y;
+                    const int64_t nq = (item0 + il) / pb.H;
+                    const float2 r = __ldg(reinterpret_cast<const float2*>(fz.ref) + nq * fz.ref_levels +
+                                           (fz.ref_levels == 1 ? 0 : l));
+                    xy = make_float2(__fadd_rn(r.x, __fdiv_rn(xy.x, (float)Wl)), __fadd_rn(r.y, __fdiv_rn(xy.y, (float)Hl)));
+                    if (fz.attn_out != nullptr) fz.attn_out[item0 * LP + s0 + u * kFwdThreads] = a;
+                }
                 const Sample sm = make_sample(xy.x, xy.y, Hl, Wl, pb.coord_mode);
                 const int xc0 = min(max(sm.x0, 0), Wl - 1), xc1 = min(max(sm.x0 + 1, 0), Wl - 1);
                 const int yc0 = min(max(sm.y0, 0), Hl - 1), yc1 = min(max(sm.y0 + 1, 0), Hl - 1);
@@ -290,19 +325,23 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     }
 }
 
+static size_t lean_smem(const Problem& pb, int ipc) {
+    return (size_t)ipc * (pb.L * pb.P * sizeof(SampleParams) + 16 + sizeof(float2));
+}
+
 template <int G, int K, bool VBF>
 static cudaError_t launch_lean(const Problem& pb, const void* value, const float* loc, const float* attn,
-                               void* out, bool out_bf16, int min_blocks, cudaStream_t st) {
+                               void* out, bool out_bf16, int min_blocks, const FusedPrologue& fz, cudaStream_t st) {
     constexpr int IPC = kFwdThreads / G;
     const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
     const unsigned grid = (unsigned)((items + IPC - 1) / IPC);
-    const size_t smem = (size_t)IPC * (pb.L * pb.P * sizeof(SampleParams) + 16);
+    const size_t smem = lean_smem(pb, IPC);
     auto launch = [&](auto kern) -> cudaError_t {
         if (smem > 48 * 1024) {
             const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out);
+        kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out, fz);
         return cudaGetLastError();
     };
     // min_blocks: occupancy target (registers per thread are capped accordingly); K == 1 only
@@ -320,16 +359,18 @@ bool forward_lean_supported(const Problem& pb, bool value_bf16) {
     if (!(nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16)) return false;
     if ((int64_t)pb.S * pb.vs_s * es >= (int64_t)0x7fffffff) return false;
     const int g = nv == 3 ? 1 : nv == 6 ? 8 : nv == 12 ? 4 : nv == 16 ? 8 : nv;
-    return (size_t)(kFwdThreads / g) * (pb.L * pb.P * sizeof(SampleParams) + 16) <= 96 * 1024;
+    return lean_smem(pb, kFwdThreads / g) <= 96 * 1024;
 }
 
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st) {
+                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st,
+                         const float* ref, int ref_levels, float* attn_out) {
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
+    const FusedPrologue fz{ref, ref_levels, attn_out};
 #define MSDA_LEAN_CASE(NV, G, K)                                                          \
     case NV:                                                                              \
-        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, min_blocks, st)  \
-                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, min_blocks, st);
+        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, min_blocks, fz, st)  \
+                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, min_blocks, fz, st);
     switch (nv) {
         MSDA_LEAN_CASE(1, 1, 1)
         MSDA_LEAN_CASE(2, 2, 1)

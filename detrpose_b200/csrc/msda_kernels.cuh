@@ -13,8 +13,10 @@ cudaError_t forward_flat(const Problem& pb, const void* value, bool value_bf16, 
                          const float* attn, void* out, bool out_bf16, cudaStream_t st);
 
 bool forward_lean_supported(const Problem& pb, bool value_bf16);
+// ref != nullptr: fused prologue -- loc = sampling offsets, attn = attention logits (see msda_fwd.cu)
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st);
+                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st,
+                         const float* ref = nullptr, int ref_levels = 1, float* attn_out = nullptr);
 
 // msda_fwd_staged.cu
 bool forward_staged_supported(const Problem& pb, bool value_bf16, bool small);
@@ -28,9 +30,14 @@ cudaError_t backward_flat(const Problem& pb, const void* value, bool value_bf16,
 
 // msda_bwd_gather.cu
 bool backward_gather_supported(const Problem& pb, bool value_bf16);
+// ref != nullptr: fused prologue -- loc = sampling offsets, grad_loc receives the gradient w.r.t. the offsets
 cudaError_t backward_gather(const Problem& pb, const void* value, bool value_bf16, const float* loc,
                             const float* attn, const void* grad_out, float* grad_value, float* grad_loc,
-                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st);
+                            float* grad_attn, int accumulate, int threads_pref, cudaStream_t st,
+                            const float* ref = nullptr, int ref_levels = 1);
+// grad_logits = a * (g - sum_j a_j g_j) per row of `cols` softmaxed weights (ms_deform_attn.py:393 backward)
+cudaError_t softmax_backward(const float* attn, const float* grad_attn, float* grad_logits, int64_t rows,
+                             int cols, cudaStream_t st);
 
 cudaError_t set_phase_buffer(unsigned long long* buf);
 

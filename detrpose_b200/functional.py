@@ -23,6 +23,7 @@ from . import _lib
 __all__ = [
     "ms_deform_attn_core", "sample_indices", "level_start_index", "locations_and_weights",
     "pack_value", "clear_repack_cache", "set_default_coord_mode", "get_default_coord_mode", "ValueList",
+    "ms_deform_attn_fused",
 ]
 
 _DTYPE_CODE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
@@ -200,7 +201,7 @@ class _HubCache:
 _hub_cache = _HubCache()
 # launch counters (tests, bench)
 stats = {"repack_launches": 0, "forward_launches": 0, "backward_launches": 0, "grad_handover": 0,
-         "unpack_launches": 0}
+         "unpack_launches": 0, "fused_forward_launches": 0}
 
 
 def clear_repack_cache() -> None:
@@ -553,3 +554,140 @@ def _locations_raw(offsets: torch.Tensor, logits: torch.Tensor, ref_points: torc
                                      _stream_ptr(off.device))
     _lib.check(rc, "msda_b200_locations")
     return loc, att
+
+
+# --------------------------------------------------------------------------
+# row f1: sampler with the prologue fused in (ms_deform_attn.py:392-393, :412-416 + core :145-193)
+# --------------------------------------------------------------------------
+_fused_ok_cache: dict = {}
+
+
+def _fused_supported(pyramid, shapes, lq, n_levels, n_points) -> bool:
+    n, _, n_heads, dh = pyramid.shape
+    key = (pyramid.dtype, tuple(pyramid.stride()[:3]), shapes, n, lq, n_heads, dh, n_levels, n_points)
+    ok = _fused_ok_cache.get(key)
+    if ok is None:
+        lib = _lib.load()
+        ok = bool(lib.msda_b200_fused_supported(_code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
+                                                _lib.i32_array([d for hw in shapes for d in hw]),
+                                                n, lq, n_heads, dh, n_levels, n_points))
+        _fused_ok_cache[key] = ok
+    return ok
+
+
+class _MSDAFused(torch.autograd.Function):
+    """out = sampler(offsets, logits, ref, token): softmax, locations and sampling in one launch per direction."""
+
+    @staticmethod
+    def forward(ctx, offsets, logits, ref, meta, hub, token):
+        shapes, n_heads, n_levels, n_points, coord_mode, out_dtype = meta
+        pyramid = hub.pyramid
+        off, lg, rf = _as_f32_contig(offsets), _as_f32_contig(logits), _as_f32_contig(ref)
+        n, lq = off.shape[:2]
+        dh = pyramid.shape[3]
+        dev = pyramid.device
+        need_bwd = any(ctx.needs_input_grad[:3]) or ctx.needs_input_grad[5]
+        attn = torch.empty((n, lq, n_heads, n_levels, n_points), dtype=torch.float32, device=dev) if need_bwd else None
+        odt = out_dtype or pyramid.dtype
+        out = torch.empty((n, lq, n_heads * dh), dtype=odt, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            rc = lib.msda_b200_forward_fused(
+                pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
+                _lib.i32_array([d for hw in shapes for d in hw]),
+                off.data_ptr(), lg.data_ptr(), rf.data_ptr(), rf.shape[2],
+                out.data_ptr(), _code(odt), attn.data_ptr() if need_bwd else None,
+                n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(dev))
+        _lib.check(rc, "msda_b200_forward_fused")
+        stats["forward_launches"] += 1
+        stats["fused_forward_launches"] += 1
+        ctx.meta, ctx.hub = meta, hub
+        ctx.in_meta = (offsets.shape, offsets.dtype, logits.shape, logits.dtype, ref.shape, ref.dtype)
+        if need_bwd:
+            ctx.save_for_backward(off, rf, attn, pyramid)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        shapes, n_heads, n_levels, n_points, coord_mode, _ = ctx.meta
+        off, rf, attn, pyramid = ctx.saved_tensors
+        hub = ctx.hub
+        off_shape, off_dtype, lg_shape, lg_dtype, ref_shape, ref_dtype = ctx.in_meta
+        need_small = any(ctx.needs_input_grad[:3])
+        need_value = ctx.needs_input_grad[5]
+        n, total, _, dh = pyramid.shape
+        lq = off.shape[1]
+        dev = pyramid.device
+        if grad_out.dtype != pyramid.dtype:
+            grad_out = grad_out.to(pyramid.dtype)
+        grad_out = grad_out.contiguous()
+        into, first = hub.buffer, hub.buffer is None
+        if need_value and first:
+            into = torch.empty((n, total, n_heads, dh), dtype=torch.float32, device=dev)
+        g_off = torch.empty((n, lq, n_heads, n_levels, n_points, 2), dtype=torch.float32, device=dev) if need_small else None
+        g_att = torch.empty_like(attn) if need_small else None
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            rc = lib.msda_b200_backward_fused(
+                pyramid.data_ptr(), _code(pyramid.dtype), _lib.i64_array(pyramid.stride()[:3]),
+                _lib.i32_array([d for hw in shapes for d in hw]),
+                off.data_ptr(), rf.data_ptr(), rf.shape[2], attn.data_ptr(),
+                grad_out.data_ptr(), _code(grad_out.dtype),
+                into.data_ptr() if need_value else None, 0 if first else 1,
+                g_off.data_ptr() if need_small else None, g_att.data_ptr() if need_small else None,
+                n, lq, n_heads, dh, n_levels, n_points, coord_mode, _stream_ptr(dev))
+            _lib.check(rc, "msda_b200_backward_fused")
+            stats["backward_launches"] += 1
+            g_lg = g_ref = None
+            if need_small and ctx.needs_input_grad[1]:
+                rc = lib.msda_b200_softmax_backward(attn.data_ptr(), g_att.data_ptr(), g_att.data_ptr(),
+                                                    n * lq * n_heads, n_levels * n_points, _stream_ptr(dev))
+                _lib.check(rc, "msda_b200_softmax_backward")
+                g_lg = g_att.reshape(lg_shape).to(lg_dtype)
+        if need_small and ctx.needs_input_grad[2]:
+            # location = ref + offset / (W_l, H_l): d/d ref = sum over heads and points (and levels when the
+            # reference point is shared) of grad_offset * (W_l, H_l)
+            norm = level_normalizer(shapes, dev).view(1, 1, 1, n_levels, 1, 2)
+            g_ref = (g_off * norm).sum(dim=(2, 4))
+            if ref_shape[2] == 1:
+                g_ref = g_ref.sum(dim=2, keepdim=True)
+            g_ref = g_ref.reshape(ref_shape).to(ref_dtype)
+        tok = None
+        if need_value:
+            hub.buffer = into
+            tok = hub.tok_grad
+        g_off_out = g_off.reshape(off_shape).to(off_dtype) if (need_small and ctx.needs_input_grad[0]) else None
+        return g_off_out, g_lg, g_ref, None, None, tok
+
+
+def ms_deform_attn_fused(value, value_spatial_shapes, offsets, logits, ref_points, *, n_heads: int,
+                         n_levels: int, n_points: int, out_dtype: torch.dtype = None,
+                         coord_mode: int = None) -> torch.Tensor:
+    """``MSDeformAttn.forward`` after its two Linears, 2-D reference points (ms_deform_attn.py:392-393,
+    :412-416, :440 -> :145-193): softmax over L*P, ``ref + offsets / (W_l, H_l)`` and the sampling core in
+    ONE launch per direction; locations and weights never reach HBM.
+
+    ``offsets`` ``(N, Lq, H*L*P*2)``, ``logits`` ``(N, Lq, H*L*P)`` (the Linear outputs, any float dtype:
+    the arithmetic is fp32), ``ref_points`` ``(N, Lq, 1|L, 2)``; ``value`` as for ``ms_deform_attn_core``.
+    Differentiable w.r.t. offsets, logits, reference points and value.  Shapes outside the fused kernels run
+    the two-step path (``locations_and_weights`` + ``ms_deform_attn_core``) with the same result."""
+    _require_cuda(offsets, "offsets")
+    shapes = _shapes_tuple(value_spatial_shapes)
+    if len(shapes) != n_levels:
+        raise ValueError(f"{len(shapes)} spatial shapes for {n_levels} levels")
+    if n_levels > _lib.MAX_LEVELS or n_points > _lib.MAX_POINTS:
+        raise ValueError(f"at most {_lib.MAX_LEVELS} levels and {_lib.MAX_POINTS} points are supported")
+    n, lq = offsets.shape[:2]
+    if offsets.numel() != n * lq * n_heads * n_levels * n_points * 2 or logits.numel() * 2 != offsets.numel():
+        raise ValueError("offsets must be (N, Lq, H*L*P*2) and logits (N, Lq, H*L*P)")
+    if ref_points.dim() != 4 or ref_points.shape[-1] != 2 or ref_points.shape[2] not in (1, n_levels):
+        raise ValueError("ref_points must be (N, Lq, 1|L, 2)")
+    hub = _get_hub(value, shapes, n_heads)
+    cm = _default_coord_mode if coord_mode is None else coord_mode
+    if not _fused_supported(hub.pyramid, shapes, lq, n_levels, n_points):
+        loc, att = locations_and_weights(offsets.float(), logits.float(), ref_points.float(), shapes, n_heads,
+                                         n_levels, n_points)
+        return _MSDACore.apply(loc, att, (shapes, n_heads, cm, out_dtype), hub, hub.token)
+    meta = (shapes, n_heads, n_levels, n_points, cm, out_dtype)
+    return _MSDAFused.apply(offsets, logits, ref_points, meta, hub, hub.token)

@@ -102,11 +102,11 @@ class MSDeformAttn(nn.Module):
             raise ValueError('Last dim of reference_points must be 2 or 4, but get {} instead.'.format(last))
 
         if last == 2 and self.fuse_prologue and offsets.is_cuda:
-            # one kernel for softmax + locations, in fp32: bit-identical to the reference's ops for fp32
-            # inputs; under autocast (bf16 / fp16 Linear outputs) the arithmetic is done in fp32 instead of
-            # the reduced precision, which only moves the locations closer to the fp32 result
-            locations, weights = MF.locations_and_weights(offsets.float(), logits.float(), ref.float(),
-                                                          shapes, H, L, P)
+            # softmax + locations + sampling in one launch per direction (row f1), in fp32: locations are
+            # bit-identical to the reference's ops for fp32 inputs; under autocast (bf16 / fp16 Linear outputs)
+            # the arithmetic is done in fp32 instead of the reduced precision, which only moves the locations
+            # closer to the fp32 result
+            return MF.ms_deform_attn_fused(value, shapes, offsets, logits, ref, n_heads=H, n_levels=L, n_points=P)
         else:
             offsets = offsets.view(N, Len_q, H, L, P, 2)
             weights = F.softmax(logits.view(N, Len_q, H, L * P), -1).view(N, Len_q, H, L, P)

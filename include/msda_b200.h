@@ -160,6 +160,53 @@ MSDA_API int msda_b200_locations(const float* offsets, const float* logits, cons
                         int N, int Lq, int H, int L, int P, void* stream);
 
 /*
+ * Sampler with the prologue fused in.  Replaces, in one launch per direction,
+ * ms_deform_attn.py:392-393 (softmax over L*P), :412-416 (ref + offsets / (W_l, H_l), 2-D reference points)
+ * and the sampling core :145-193.  Locations and weights are computed with the arithmetic of
+ * msda_b200_locations (divide and add separately rounded: corner indices stay bit-exact) and never reach HBM.
+ *
+ * offsets        device fp32 (N, Lq, H, L, P, 2)  (output of the sampling_offsets Linear), 16-byte aligned
+ * logits         device fp32 (N, Lq, H, L*P)      (output of the attention_weights Linear), 16-byte aligned
+ * ref_points     device fp32 (N, Lq, ref_levels, 2), ref_levels 1 (broadcast over levels) or L, 8-byte aligned
+ * attention_out  device fp32 (N, Lq, H, L, P) or NULL: the softmaxed weights, kept for the backward
+ *
+ * Shapes the fused kernels do not cover return MSDA_ERR_SHAPE (query with msda_b200_fused_supported; the
+ * caller then runs msda_b200_locations + msda_b200_forward / _backward).
+ */
+MSDA_API int msda_b200_fused_supported(int value_dtype, const int64_t* value_strides,
+                              const int32_t* spatial_shapes, int N, int Lq, int H, int Dh, int L, int P);
+
+MSDA_API int msda_b200_forward_fused(const void* value, int value_dtype, const int64_t* value_strides,
+                            const int32_t* spatial_shapes,
+                            const float* offsets, const float* logits, const float* ref_points, int ref_levels,
+                            void* out, int out_dtype, float* attention_out,
+                            int N, int Lq, int H, int Dh, int L, int P,
+                            int coord_mode, void* stream);
+
+/*
+ * Backward of the fused sampler.  `attention` is attention_out of the forward.  grad_offsets (shape of
+ * offsets, 32-byte aligned) is the gradient w.r.t. the sampling offsets -- the (W_l, H_l) of the pixel
+ * mapping and of `offsets / (W_l, H_l)` cancel; grad_attention is the gradient w.r.t. the softmaxed weights:
+ * msda_b200_softmax_backward turns it into the gradient w.r.t. the logits (the sum over L*P spans several
+ * CTAs of the backward, hence a pass of its own).  The gradient w.r.t. ref_points is the sum of
+ * grad_offsets * (W_l, H_l) over heads, (levels,) points; DETRPose detaches them (transformer.py:1246).
+ */
+MSDA_API int msda_b200_backward_fused(const void* value, int value_dtype, const int64_t* value_strides,
+                             const int32_t* spatial_shapes,
+                             const float* offsets, const float* ref_points, int ref_levels,
+                             const float* attention,
+                             const void* grad_out, int grad_out_dtype,
+                             float* grad_value, int accumulate, float* grad_offsets, float* grad_attention,
+                             int N, int Lq, int H, int Dh, int L, int P,
+                             int coord_mode, void* stream);
+
+/* grad_logits[r, i] = attention[r, i] * (grad_attention[r, i] - sum_j attention[r, j] * grad_attention[r, j])
+ * for `rows` = N*Lq*H rows of `cols` = L*P contiguous fp32 values (all three buffers 16-byte aligned;
+ * grad_logits may alias grad_attention). */
+MSDA_API int msda_b200_softmax_backward(const float* attention, const float* grad_attention, float* grad_logits,
+                               int64_t rows, int cols, void* stream);
+
+/*
  * Repack the reference's per-level strided views into one channel-last pyramid.
  *
  * level_ptrs     host[L] of device pointers: element (nh=0, c=0, s=0) of value[l]

@@ -3,13 +3,16 @@ built from the vendored sources (baseline/_ref), run with and without this packa
 same weights, same inputs, same GPU.
 
 Inference: DETRPose-N/S/L/X, deploy()+eval() as tools/benchmark/torch_benchmark.py:82-93 does, fp32, batch 2.
-Training: DETRPose-S forward in train mode with OKS-denoising queries (dn_component.py:39), the reference
-criterion (Hungarian matching on the CPU), backward -- loss and parameter gradients compared.
+Training: DETRPose-S forward in train mode with OKS-denoising queries (dn_component.py:39) under bf16
+autocast as `--amp` runs it (engine.py:50; without autocast the reference's own decoder layer trips autograd's
+in-place check, transformer.py:360-370, so fp32 training is not a configuration the reference supports), the
+reference criterion in fp32 (Hungarian matching on the CPU), backward -- loss and parameter gradients compared.
 
 Tolerances (fp32): outputs 2e-4 of max|ref| -- the sampler itself is within 1e-5 (tests/test_gpu_parity.py);
 the rest is fp32 reassociation (fused gate / LQE epilogues, accumulation order) amplified through 3-6 decoder
-layers of LayerNorms.  Parameter gradients 2e-3 of the per-tensor max (they pass through the same stack and
-the criterion's matched-pair selection).
+layers of LayerNorms.  Training under bf16 autocast: both arms round to bf16 at different places (the
+reference's sampler returns fp32 that the next Linear rounds, the kernels store bf16), so the loss is held to
+2e-2 relative and every large parameter gradient to a cosine similarity of 0.98 with the reference's.
 """
 import pytest
 import torch
@@ -72,8 +75,10 @@ def test_inference_core_only_patch_list_interface():
 def _train_pass(model, criterion, x, targets, seed):
     model.zero_grad(set_to_none=True)
     torch.manual_seed(seed)                      # the denoising queries draw noise (dn_component.py:78-112)
-    out = model(x, targets)
-    loss_dict = criterion(out, targets)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = model(x, targets)
+    with torch.autocast("cuda", enabled=False):
+        loss_dict = criterion(out, targets)
     loss = sum(loss_dict.values()) + model.layer_loss.to(x.device)
     loss.backward()
     grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
@@ -94,9 +99,15 @@ def test_training_step_loss_and_gradients_match_unpatched_reference():
     assert d["forward_launches"] == 3 and d["backward_launches"] == 3, d
     assert d["repack_launches"] == 0 and d["unpack_launches"] == 0 and d["grad_handover"] == 1, d
     assert out_got["pred_keypoints"].shape == out_ref["pred_keypoints"].shape     # includes the DN queries
-    assert abs(loss_got - loss_ref) <= 2e-4 * abs(loss_ref), (loss_got, loss_ref)
+    assert abs(loss_got - loss_ref) <= 2e-2 * abs(loss_ref), (loss_got, loss_ref)
     assert set(grads_got) == set(grads_ref)
-    top = max(float(g.abs().max()) for g in grads_ref.values())
-    worst = max((rel_err(grads_got[n].cpu().numpy(), g.cpu().numpy()), n) for n, g in grads_ref.items()
-                if float(g.abs().max()) > 1e-6 * top)             # skip tensors that are numerically zero
-    assert worst[0] <= 2e-3, worst
+    norms = {n: float(g.float().norm()) for n, g in grads_ref.items()}
+    top = max(norms.values())
+    cos = {n: float(torch.nn.functional.cosine_similarity(grads_got[n].float().flatten(),
+                                                          grads_ref[n].float().flatten(), dim=0))
+           for n in grads_ref if norms[n] > 1e-3 * top and grads_ref[n].numel() >= 256}
+    # (the tensors that carry the update; scalar / tiny parameters are sums with heavy cancellation whose sign
+    # is noise under bf16 autocast in either arm)
+    assert len(cos) >= 20, len(cos)
+    worst = min((c, n) for n, c in cos.items())
+    assert worst[0] >= 0.98, worst
