@@ -134,7 +134,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ONE: the whole query range fits one chunk and grad_value is overwritten -- the common case; the
 // read-modify-write paths and the chunk bookkeeping compile away (less register pressure).
-template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, int MODE = 0>
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, 1)
 bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float* __restrict__ loc,
                   const float* __restrict__ attn, const char* __restrict__ grad_out,
@@ -212,7 +212,6 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const int npix = Hl * Wl;
     const float inv_w = 1.0f / (float)Wl;
     const float fW = (float)Wl, fH = (float)Hl;
-    const float sW = ref != nullptr ? 1.0f : fW, sH = ref != nullptr ? 1.0f : fH;
     // (q, p) of sample tid and the step to sample tid + THREADS
     const int q_t0 = tid / P, p_t0 = tid - q_t0 * P;
     const int dq = THREADS / P, dp = THREADS - dq * P;
@@ -284,7 +283,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
             for (int i = tid; i < nsamp; i += THREADS) {
                 float2 xy = loc_s[i];
                 const float a = att_s[i];
-                if (ref != nullptr) {
+                if constexpr (FUSED) {
                     // fused prologue (row f1): the staged pairs are sampling offsets; location = ref + offset /
                     // (W_l, H_l) with the divide and the add rounded separately (ms_deform_attn.py:414-416)
                     const float2 r = __ldg(reinterpret_cast<const float2*>(ref) +
@@ -463,38 +462,6 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             ga_m = ((id >> 16) & 0xfffu) * (VPR * 16);
                         }
                         float d[4];
-                        if constexpr (MODE == 1) {
-                            // software-pipelined batch: the 8 broadcasts and the 4 g-row loads of the batch are
-                            // issued before the first FMA (idle slots read the zero row with weight zero), so a
-                            // warp exposes one shuffle + one shared-load latency per batch instead of per visit
-                            float w4[4];
-                            uint32_t ga4[4];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                w4[u] = __shfl_sync(FULL, w_m, u, 4);
-                                ga4[u] = __shfl_sync(FULL, ga_m, u, 4);
-                            }
-                            uint4 graw[4][K];
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-#pragma unroll
-                                for (int k = 0; k < K; ++k) graw[u][k] = lds_u4(a_g + ga4[u] + k * G * 16);
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                float2 d2 = make_float2(0.0f, 0.0f);
-#pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    float2 g[E2];
-                                    unpack2<VBF>(graw[u][k], g);
-#pragma unroll
-                                    for (int c = 0; c < E2; ++c) {
-                                        if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
-                                        acc[k * E2 + c] = fma2(g[c], make_float2(w4[u], w4[u]), acc[k * E2 + c]);
-                                    }
-                                }
-                                d[u] = d2.x + d2.y;
-                            }
-                        } else {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             d[u] = 0.0f;
@@ -514,7 +481,6 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                                 }
                                 d[u] = d2.x + d2.y;
                             }
-                        }
                         }
                         if (SMALL) {
                             const bool hi2 = lane & 2, hi1 = lane & 1;
@@ -685,6 +651,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         // write path is bound by the number of store transactions, not by bytes.
         if (SMALL) {
             const int nrec = (int)lds_u16(a_ends + nbins * 2);          // end of the last bin
+            const float sW = FUSED ? 1.0f : fW, sH = FUSED ? 1.0f : fH;
             for (int e = tid; e < nrec; e += THREADS) {
                 const float4 rec = rec_s[e];
                 const unsigned id = __float_as_uint(rec.w);
@@ -743,11 +710,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
 static thread_local const float* g_fused_ref = nullptr;
 static thread_local int g_fused_ref_levels = 1;
 
-template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, int MODE = 0>
+template <int G, int K, bool VBF, int THREADS, bool SMALL, bool ONE, bool FUSED>
 static cudaError_t launch_gather_impl(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
                                       const float* attn, const void* go, float* gv, float* gl, float* ga,
                                       int accumulate, cudaStream_t st, const float* ref, int ref_levels) {
-    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL, ONE, MODE>;
+    auto kern = bwd_gather_kernel<G, K, VBF, THREADS, SMALL, ONE, FUSED>;
     static thread_local int configured_for = -1;      // per-thread cache of the attribute call (per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -762,17 +729,28 @@ static cudaError_t launch_gather_impl(const Problem& pb, const GatherPlan& plan,
     return cudaGetLastError();
 }
 
-template <int G, int K, bool VBF, int THREADS, int MODE = 0>
-static cudaError_t launch_gather(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
-                                 const float* attn, const void* go, float* gv, float* gl, float* ga,
-                                 int accumulate, cudaStream_t st) {
+template <int G, int K, bool VBF, int THREADS, bool FUSED>
+static cudaError_t launch_gather_f(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
+                                   const float* attn, const void* go, float* gv, float* gl, float* ga,
+                                   int accumulate, cudaStream_t st) {
     const bool one = plan.n_chunks == 1 && !accumulate;
     const float* ref = g_fused_ref;
     const int rl = g_fused_ref_levels;
     if (gl != nullptr)
-        return one ? launch_gather_impl<G, K, VBF, THREADS, true, true, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl)
-                   : launch_gather_impl<G, K, VBF, THREADS, true, false, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
-    return launch_gather_impl<G, K, VBF, THREADS, false, false, MODE>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
+        return one ? launch_gather_impl<G, K, VBF, THREADS, true, true, FUSED>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl)
+                   : launch_gather_impl<G, K, VBF, THREADS, true, false, FUSED>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
+    return launch_gather_impl<G, K, VBF, THREADS, false, false, FUSED>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st, ref, rl);
+}
+
+template <int G, int K, bool VBF, int THREADS>
+static cudaError_t launch_gather(const Problem& pb, const GatherPlan& plan, const void* value, const float* loc,
+                                 const float* attn, const void* go, float* gv, float* gl, float* ga,
+                                 int accumulate, cudaStream_t st) {
+    // the fused-prologue form (reference points given) is a compile-time variant: the default kernel carries
+    // none of its code or registers
+    return g_fused_ref != nullptr
+        ? launch_gather_f<G, K, VBF, THREADS, true>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st)
+        : launch_gather_f<G, K, VBF, THREADS, false>(pb, plan, value, loc, attn, go, gv, gl, ga, accumulate, st);
 }
 
 // Returns false when the shape does not fit the gather kernel (caller falls back to the flat one).
@@ -830,24 +808,6 @@ static cudaError_t backward_gather_dispatch(const Problem& pb, const void* value
     if (!make_plan(pb, pb.Dh * (value_bf16 ? 2 : 4), plan)) return cudaErrorInvalidValue;
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
     const bool wide_regs = threads_pref == 512;
-    // experimental instantiations (bf16, Dh = 32 only), selected through msda_b200_set_variant(_, 10..14)
-    if (threads_pref >= 10 && threads_pref <= 14 && nv == 4 && value_bf16) {
-#define MSDA_X(G_, K_, T_, M_) return launch_gather<G_, K_, true, T_, M_>(pb, plan, value, loc, attn, grad_out, \
-                                                                       grad_value, grad_loc, grad_attn, accumulate, st)
-        switch (threads_pref) {
-            case 10: MSDA_X(2, 2, 512, 0);
-            case 11: MSDA_X(2, 2, 768, 0);
-            case 12: MSDA_X(4, 1, 1024, 1);
-            case 13: MSDA_X(4, 1, 768, 1);
-            case 14: MSDA_X(4, 1, 512, 1);
-        }
-#undef MSDA_X
-    }
-    if (threads_pref == 768 && nv == 4)          // 768 threads x 85 registers
-        return value_bf16 ? launch_gather<4, 1, true, 768>(pb, plan, value, loc, attn, grad_out, grad_value,
-                                                           grad_loc, grad_attn, accumulate, st)
-                          : launch_gather<4, 1, false, 768>(pb, plan, value, loc, attn, grad_out, grad_value,
-                                                            grad_loc, grad_attn, accumulate, st);
     if (wide_regs) {          // 512 threads x 128 registers instead of 1024 x 64
 #define MSDA_GATHER_WIDE(NV, G, K)                                                                          \
     case NV:                                                                                                \

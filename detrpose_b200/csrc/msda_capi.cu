@@ -182,13 +182,12 @@ MSDA_API int msda_b200_backward(const void* value, int value_dtype, const int64_
     // registers); variant 0: flat + vector reductions
     const int variant = g_bwd_variant.load();
     const bool can_gather = grad_out_dtype == value_dtype && msda::backward_gather_supported(pb, vbf);
-    if ((variant == 1 || variant == 2 || variant == 3 || variant >= 10) && !can_gather)
+    if ((variant == 1 || variant == 2) && !can_gather)
         return fail(MSDA_ERR_SHAPE, "gather-form backward does not support this shape/dtype combination");
     cudaError_t e;
     if (can_gather && variant != 0) {
         e = msda::backward_gather(pb, value, vbf, locations, attention, grad_out, grad_value, grad_locations,
-                                  grad_attention, accumulate,
-                                  variant >= 10 ? variant : variant == 2 ? 512 : variant == 3 ? 768 : 1024, st);
+                                  grad_attention, accumulate, variant == 2 ? 512 : 1024, st);
     } else {
         if (grad_value && !accumulate) {
             e = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * pb.S * H * Dh, st);
@@ -263,8 +262,7 @@ MSDA_API int msda_b200_backward_fused(const void* value, int value_dtype, const 
     const int variant = g_bwd_variant.load();
     const cudaError_t e = msda::backward_gather(pb, value, vbf, offsets, attention, grad_out, grad_value, grad_offsets,
                                                 grad_attention, accumulate,
-                                                variant >= 10 ? variant : variant == 2 ? 512 : variant == 3 ? 768 : 1024,
-                                                (cudaStream_t)stream, ref_points, ref_levels);
+                                                variant == 2 ? 512 : 1024, (cudaStream_t)stream, ref_points, ref_levels);
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_backward_fused launch");
 }
 
