@@ -200,8 +200,9 @@ def test_random_shapes_against_reference_ops_on_device(bwd_variant):
             out = dp.ms_deform_attn_core(otorch.make_value_list(mem, H, shapes), shapes, loc, att)
             got_g = torch.autograd.grad(out, [mem, loc, att], inp["grad_out"])
         except _lib.MSDAError as exc:
-            if "does not support this shape" in str(exc):
-                continue                                  # a forced variant refuses this shape (loudly)
+            from conftest import MAY_REFUSE
+            if MAY_REFUSE.get(tuple(bwd_variant), "\0") in str(exc):
+                continue                                  # an opt-in variant refuses this shape (loudly)
             raise
         ia, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_UNFUSED)
         ib, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_FMA)
@@ -467,3 +468,113 @@ def test_module_under_bf16_autocast_uses_fused_prologue_and_tracks_fp32():
     got.float().square().mean().backward()
     assert query.grad is not None and memory.grad is not None and m.sampling_offsets.weight.grad is not None
     assert torch.isfinite(query.grad).all() and torch.isfinite(memory.grad).all()
+
+
+# --------------------------------------------------------------------------------------------------
+# Round-2 additions: the bench configuration itself, the training-time pyramids, the big sweep point,
+# tiny attention weights (VERDICT r01 "What's weak" 1-4)
+# --------------------------------------------------------------------------------------------------
+def _device_reference(w_shapes, H, mem, loc, att, go):
+    """The reference's op sequence on the device (fp32), value handed over as its own strided list."""
+    m = mem.detach().float().requires_grad_(True)
+    l = loc.detach().requires_grad_(True)
+    a = att.detach().requires_grad_(True)
+    out = otorch.core(otorch.make_value_list(m, H, w_shapes), w_shapes, l, a)
+    g = torch.autograd.grad(out, [m, l, a], go.float())
+    return out.detach(), g
+
+
+def _floor_agree(loc, shapes):
+    ia, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_UNFUSED)
+    ib, _ = dp.sample_indices(loc.detach(), shapes, coord_mode=_lib.COORD_FMA)
+    return (ia == ib).all(-1, keepdim=True).float()
+
+
+@pytest.mark.parametrize("layout", ["memory", "reference"])
+@pytest.mark.parametrize("vdt", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_bench_configuration_against_reference_ops(vdt, layout):
+    """Exactly what bench.py times -- DETRPose-S shape, batch 64, bf16 (and fp32) storage, zero-copy memory and
+    the reference's strided list -- held against the reference's ops on the same device."""
+    w = synthetic.WORKLOADS["detrpose_s"]
+    N = 64
+    inp = synthetic.make_inputs(N, w["Lq"], w["H"], w["Dh"], w["shapes"], w["P"], seed=0, device=DEV, value_dtype=vdt)
+    ref_out, ref_g = _device_reference(w["shapes"], w["H"], inp["memory"], inp["locations"], inp["attention"],
+                                       inp["grad_out"])
+    mem = inp["memory"].clone().requires_grad_(True)
+    loc = inp["locations"].clone().requires_grad_(True)
+    att = inp["attention"].clone().requires_grad_(True)
+    value = mem if layout == "memory" else otorch.make_value_list(mem, w["H"], w["shapes"])
+    out = dp.ms_deform_attn_core(value, w["shapes"], loc, att)
+    gm, gl, ga = torch.autograd.grad(out, [mem, loc, att], inp["grad_out"])
+    keep = _floor_agree(loc, w["shapes"])
+    # bf16 storage: output and the returned value gradient carry one bf16 rounding; the fp32 results 1e-5
+    tol_store = 2.0 ** -8 if vdt == torch.bfloat16 else TOL
+    assert rel_err(out.detach().float().cpu().numpy(), ref_out.cpu().numpy()) <= tol_store
+    assert rel_err(gm.float().cpu().numpy(), ref_g[0].cpu().numpy()) <= tol_store
+    assert rel_err((gl * keep).cpu().numpy(), (ref_g[1] * keep).cpu().numpy()) <= TOL
+    assert rel_err(ga.cpu().numpy(), ref_g[2].cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("shapes", [((100, 100), (50, 50), (25, 25)), ((60, 60), (30, 30), (15, 15)),
+                                    ((100, 75), (50, 38), (25, 19))], ids=["800px", "480px", "800x600px"])
+@pytest.mark.parametrize("Lq", [1476, 1584, 1800])
+@pytest.mark.parametrize("vdt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_training_pyramids_and_denoising_lengths(shapes, Lq, vdt):
+    """Multi-scale collate gives 480..800 px inputs (src/data/dataloader.py:56-61,103-105) and the denoising
+    queries Len_q = (pad + 60) * 18 (dn_component.py:54-63): several query chunks, 101 x 101 bins."""
+    H, Dh, P, N = 8, 32, 4, 2
+    inp = synthetic.make_inputs(N, Lq, H, Dh, shapes, P, seed=Lq, device=DEV, value_dtype=vdt)
+    ref_out, ref_g = _device_reference(shapes, H, inp["memory"], inp["locations"], inp["attention"], inp["grad_out"])
+    mem = inp["memory"].clone().requires_grad_(True)
+    loc = inp["locations"].clone().requires_grad_(True)
+    att = inp["attention"].clone().requires_grad_(True)
+    out = dp.ms_deform_attn_core(mem, shapes, loc, att)
+    gm, gl, ga = torch.autograd.grad(out, [mem, loc, att], inp["grad_out"])
+    keep = _floor_agree(loc, shapes)
+    tol_store = 2.0 ** -8 if vdt == torch.bfloat16 else TOL
+    assert rel_err(out.detach().float().cpu().numpy(), ref_out.cpu().numpy()) <= tol_store
+    assert rel_err(gm.float().cpu().numpy(), ref_g[0].cpu().numpy()) <= tol_store
+    assert rel_err((gl * keep).cpu().numpy(), (ref_g[1] * keep).cpu().numpy()) <= TOL
+    assert rel_err(ga.cpu().numpy(), ref_g[2].cpu().numpy()) <= TOL
+
+
+def test_sweep4_batch32_lq3000():
+    """BASELINE configs[4] corner: 4 levels, Len_q 3000 (three query chunks), batch 32, fp32."""
+    w = synthetic.WORKLOADS["sweep4"]
+    N, Lq = 32, 3000
+    inp = synthetic.make_inputs(N, Lq, w["H"], w["Dh"], w["shapes"], w["P"], seed=4, device=DEV)
+    ref_out, ref_g = _device_reference(w["shapes"], w["H"], inp["memory"], inp["locations"], inp["attention"],
+                                       inp["grad_out"])
+    mem = inp["memory"].clone().requires_grad_(True)
+    loc = inp["locations"].clone().requires_grad_(True)
+    att = inp["attention"].clone().requires_grad_(True)
+    out = dp.ms_deform_attn_core(otorch.make_value_list(mem, w["H"], w["shapes"]), w["shapes"], loc, att)
+    gm, gl, ga = torch.autograd.grad(out, [mem, loc, att], inp["grad_out"])
+    keep = _floor_agree(loc, w["shapes"])
+    assert rel_err(out.detach().cpu().numpy(), ref_out.cpu().numpy()) <= TOL
+    assert rel_err(gm.cpu().numpy(), ref_g[0].cpu().numpy()) <= TOL
+    assert rel_err((gl * keep).cpu().numpy(), (ref_g[1] * keep).cpu().numpy()) <= TOL
+    assert rel_err(ga.cpu().numpy(), ref_g[2].cpu().numpy()) <= TOL
+
+
+@pytest.mark.parametrize("tiny", [1e-20, 1e-31, 0.0, -1e-31])
+def test_tiny_attention_weights(tiny, bwd_variant):
+    """Samples whose weight is below 1e-30 in magnitude are finished outside the pixel pass of the gather
+    backward (msda_bwd_gather.cu, P1): their contribution to grad_value / grad_locations (< 1e-30 |grad_out|)
+    is dropped, grad_attention is still exact.  1e-20 takes the normal path.  Either way every gradient
+    stays within 1e-5 of max|ref|, and nothing becomes NaN (the weight is recovered by a division)."""
+    c = load_core_case("s_like")
+    att = c["attention"].copy()
+    rng = np.random.default_rng(7)
+    mask = rng.random(att.shape) < 0.25
+    att[mask] = tiny
+    c2 = dict(c, attention=att)
+    out, gm, gl, ga = _run(c2, "reference")
+    a_out, a_gm, a_gl, a_ga = _arbiter(c2)
+    for got in (out, gm, gl, ga):
+        assert np.isfinite(got).all()
+    assert rel_err(out, a_out) <= TOL and rel_err(gm, a_gm) <= TOL
+    assert rel_err(gl, a_gl) <= TOL and rel_err(ga, a_ga) <= TOL
+    # absolute worst case of the dropped contributions: below 1e-30 * |grad_out| * |value| per sample
+    if abs(tiny) < 1e-30:
+        assert np.abs(gl[mask] - a_gl[mask]).max() <= 1e-25
