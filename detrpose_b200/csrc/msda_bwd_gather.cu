@@ -93,6 +93,19 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
     return r;
 }
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, const float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned lds_u16(uint32_t a) {
     unsigned short r;
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
@@ -183,7 +196,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
     const SmemLayout lay(q_chunk, P, row_bytes, bins_words_max);
     float4* rec_s = reinterpret_cast<float4*>(smem + lay.off_rec);
     float* dots_s = reinterpret_cast<float*>(smem + lay.off_dots);
-    float4* tmp_s = reinterpret_cast<float4*>(smem + lay.off_dots);      // unsorted records live here until P4
+    // the unsorted records live in the dots region (a_dots) until P4
     unsigned* bins = reinterpret_cast<unsigned*>(smem + lay.off_bins);
     unsigned* scan_s = reinterpret_cast<unsigned*>(smem + lay.off_scan);
     int* work_s = reinterpret_cast<int*>(smem + lay.off_order + 32 * 32);
@@ -231,19 +244,22 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         //      locations / attention, so that no phase below waits on a dependent global load ----
         // staging area for locations (8 B/sample) and attention (4 B/sample): the sorted-record region,
         // which is free until P3 and again after P4
-        const float2* loc_s = reinterpret_cast<const float2*>(smem + lay.off_rec);
-        const float* att_s = reinterpret_cast<const float*>(smem + lay.off_rec + nsamp * 8);
+        // (locations at a_rec, attention weights behind them: read in P1 through the shared-window addresses)
         auto stage_samples = [&]() {
             if ((P & 3) == 0) {
                 // a query's P samples are contiguous: 16-byte copies (2 per 4 locations, 1 per 4 weights)
                 const int vq = P / 4;                                // 16-byte attention vectors per query
+                // locations: the two 16-byte halves of a 32-byte piece go to neighbouring lanes, so one warp
+                // instruction touches 16 lines instead of 32 (the SM's cost is per line, not per byte)
+                for (int j = tid; j < 2 * qc * vq; j += THREADS) {
+                    const int i = j >> 1, half = j & 1;
+                    const int q = i / vq, v = i - q * vq;
+                    cp_async16(a_rec + (q * P + v * 4) * 8 + half * 16,
+                               reinterpret_cast<const float2*>(loc) + s0 + q * sstride + v * 4 + half * 2);
+                }
                 for (int i = tid; i < qc * vq; i += THREADS) {
                     const int q = i / vq, v = i - q * vq;
-                    const int64_t sidx = s0 + q * sstride + v * 4;
-                    const int si = q * P + v * 4;
-                    cp_async16(a_rec + si * 8, reinterpret_cast<const float2*>(loc) + sidx);
-                    cp_async16(a_rec + si * 8 + 16, reinterpret_cast<const float2*>(loc) + sidx + 2);
-                    cp_async16(a_rec + nsamp * 8 + si * 4, attn + sidx);
+                    cp_async16(a_rec + nsamp * 8 + (q * P + v * 4) * 4, attn + s0 + q * sstride + v * 4);
                 }
             } else {
                 int q = q_t0, p = p_t0;
@@ -279,10 +295,10 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         // (no valid corner, or |A| < 1e-30 so that wy cannot be recovered from A*wy later: their
         // contribution to grad_value / grad_locations is below 1e-30 |grad_out| and is dropped) are finished here.
         {
-            int q = q_t0, p = p_t0;
-            for (int i = tid; i < nsamp; i += THREADS) {
-                float2 xy = loc_s[i];
-                const float a = att_s[i];
+            const uint32_t a_att = a_rec + nsamp * 8;          // shared-window addresses: nothing to rebuild per sample
+            auto sample = [&](const int i, const int q) {
+                float2 xy = lds_f2(a_rec + i * 8);
+                const float a = lds_f32(a_att + i * 4);
                 if constexpr (FUSED) {
                     // fused prologue (row f1): the staged pairs are sampling offsets; location = ref + offset /
                     // (W_l, H_l) with the divide and the add rounded separately (ms_deform_attn.py:414-416)
@@ -308,7 +324,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             ((((int64_t)n * pb.Lq + q0 + q) * pb.H + h) * pb.Dh) * ES;
                         const char* vl = value + ((int64_t)n * pb.vs_n + (int64_t)pb.geom.start[l] * pb.vs_s +
                                                   (int64_t)h * pb.vs_h) * ES;
-                        const float wk[4] = {s.w_nw, s.w_ne, s.w_sw, s.w_se};
+                        // (the corner products are only needed here: the common path never computes them)
+                        const float wk[4] = {(s.vx0 & s.vy0) ? __fmul_rn(s.wx0, s.wy0) : 0.0f,
+                                             (s.vx1 & s.vy0) ? __fmul_rn(s.wx1, s.wy0) : 0.0f,
+                                             (s.vx0 & s.vy1) ? __fmul_rn(s.wx0, s.wy1) : 0.0f,
+                                             (s.vx1 & s.vy1) ? __fmul_rn(s.wx1, s.wy1) : 0.0f};
                         const int px[4] = {s.x0, s.x0 + 1, s.x0, s.x0 + 1};
                         const int py[4] = {s.y0, s.y0, s.y0 + 1, s.y0 + 1};
                         for (int k = 0; k < 4; ++k) {
@@ -327,7 +347,11 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                     }
                     t.x = ga;                                // final {grad_attn, grad_loc = 0} of this sample
                 }
-                tmp_s[i] = t;
+                sts_f4(a_dots + i * 16, t);
+            };
+            int q = q_t0, p = p_t0;
+            for (int i = tid; i < nsamp; i += THREADS) {
+                sample(i, q);
                 q += dq; p += dp;
                 if (p >= P) { p -= P; ++q; }
             }
@@ -376,7 +400,7 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
         {
             int q = q_t0, p = p_t0;
             for (int i = tid; i < nsamp; i += THREADS) {
-                float4 r = tmp_s[i];
+                float4 r = lds_f4(a_dots + i * 16);
                 const int packed = __float_as_int(r.w);
                 if (packed != 0) {
                     const int b = packed & 0xfffff;
@@ -461,26 +485,30 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                             slot_m = a_dots + (id & 0xffffu) * 16u + (up ? 0u : 8u) + (isx1 ? 4u : 0u);
                             ga_m = ((id >> 16) & 0xfffu) * (VPR * 16);
                         }
-                        float d[4];
+                        float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                        // the visits of a batch in one fall-through switch on the (warp-uniform) number that is
+                        // left: one compare chain per batch instead of a test and a branch per visit
+                        auto visit = [&](const int u) {
+                            const float w = __shfl_sync(FULL, w_m, u, 4);
+                            const uint32_t ga = __shfl_sync(FULL, ga_m, u, 4);
+                            float2 d2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            d[u] = 0.0f;
-                            if (t + u < trips) {                              // warp-uniform
-                                const float w = __shfl_sync(FULL, w_m, u, 4);
-                                const uint32_t ga = __shfl_sync(FULL, ga_m, u, 4);
-                                float2 d2 = make_float2(0.0f, 0.0f);
+                            for (int k = 0; k < K; ++k) {
+                                float2 g[E2];
+                                unpack2<VBF>(lds_u4(a_g + ga + k * G * 16), g);
 #pragma unroll
-                                for (int k = 0; k < K; ++k) {
-                                    float2 g[E2];
-                                    unpack2<VBF>(lds_u4(a_g + ga + k * G * 16), g);
-#pragma unroll
-                                    for (int c = 0; c < E2; ++c) {
-                                        if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
-                                        acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
-                                    }
+                                for (int c = 0; c < E2; ++c) {
+                                    if (SMALL) d2 = fma2(v[k * E2 + c], g[c], d2);
+                                    acc[k * E2 + c] = fma2(g[c], make_float2(w, w), acc[k * E2 + c]);
                                 }
-                                d[u] = d2.x + d2.y;
                             }
+                            d[u] = d2.x + d2.y;
+                        };
+                        switch (min(trips - t, 4)) {
+                            case 4: visit(3);
+                            case 3: visit(2);
+                            case 2: visit(1);
+                            default: visit(0);
                         }
                         if (SMALL) {
                             const bool hi2 = lane & 2, hi1 = lane & 1;
@@ -574,7 +602,10 @@ bwd_gather_kernel(const Problem pb, const char* __restrict__ value, const float*
                 // sparse level: warps fetch tiles of 32 pixels; each lane reads the bounds of one pixel,
                 // the pixels are ranked by record count and handed to the groups in that order, so the
                 // UPW pixels processed together carry similar work
-                // 32 pixels per tile (one per lane), 16 when the level has fewer tiles than warps
+                // 32 pixels per tile (one per lane), 16 when the level has fewer tiles than warps.  (Tile sizes that
+                // make the tile count a multiple of the warp count -- 25 pixels for a 40 x 40 level -- were measured:
+                // the wait at the barrier that ends P4 shrinks, but tiles that are not a multiple of the 8 pixels a
+                // warp processes together waste more slots than that saves: 513 vs 469 us.)
                 const int tpx = npix >= NWARPS * 32 ? 32 : 16;
                 const int ntiles = (npix + tpx - 1) / tpx;
                 for (;;) {
