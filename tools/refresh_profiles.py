@@ -1,10 +1,14 @@
 """Copy the round's measurement artefacts from gpurun_out/ into profiles/ (tracked) and condense the
-ncu reports (needs `ncu` on PATH; reads gpurun_out/r01_full.ncu-rep and gpurun_out/r01_launches.csv)."""
+ncu reports (needs `ncu` on PATH; reads gpurun_out/<tag>_full.ncu-rep and gpurun_out/<tag>_launches.csv).
+
+    python tools/refresh_profiles.py [r02]
+"""
 import csv
 import json
 import os
 import shutil
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
@@ -27,10 +31,14 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
 
 
 def main():
-    for src, dst in COPY.items():
-        if os.path.exists(os.path.join(G, src)):
-            shutil.copy(os.path.join(G, src), os.path.join(P, dst))
-    rep = os.path.join(G, "r01_full.ncu-rep")
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    if tag == "r01":
+        for src, dst in COPY.items():
+            if os.path.exists(os.path.join(G, src)):
+                shutil.copy(os.path.join(G, src), os.path.join(P, dst))
+    elif os.path.exists(os.path.join(G, f"{tag}_launches.csv")):
+        shutil.copy(os.path.join(G, f"{tag}_launches.csv"), os.path.join(P, f"{tag}_ncu_launch_list.csv"))
+    rep = os.path.join(G, f"{tag}_full.ncu-rep")
     if os.path.exists(rep):
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
@@ -41,7 +49,7 @@ def main():
             if k in hdr:
                 i = hdr.index(k)
                 out.append([k, units[i]] + [d[i] for d in data])
-        with open(os.path.join(P, "r01_ncu_full_summary.csv"), "w", newline="") as f:
+        with open(os.path.join(P, f"{tag}_ncu_full_summary.csv"), "w", newline="") as f:
             csv.writer(f).writerows(out)
 
         def val(d, k):
@@ -54,10 +62,10 @@ def main():
             traffic[key] = int(val(d, 'dram__bytes_read.sum') + val(d, 'dram__bytes_write.sum'))
             print(name[:45], d[hdr.index('gpu__time_duration.sum')], "us", round(traffic[key] / 1e6, 1), "MB dram, issue",
                   d[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')], "%, inst", d[hdr.index('smsp__inst_executed.sum')])
-        traffic['source'] = ('profiles/r01_ncu_full_summary.csv (ncu --set full, bench.py --steps 3 --warmup 3, '
+        traffic['source'] = (f'profiles/{tag}_ncu_full_summary.csv (ncu --set full, bench.py --steps 3 --warmup 3, '
                              'batch 64, bf16)')
         json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
-    ll = os.path.join(P, "r01_ncu_launch_list.csv")
+    ll = os.path.join(P, f"{tag}_ncu_launch_list.csv")
     if os.path.exists(ll):
         rows = list(csv.DictReader(l for l in open(ll) if l.startswith('"')))
         out = []
@@ -67,7 +75,7 @@ def main():
             out.append((r['ID'], short, r['Grid Size'], r['Block Size'], float(r['Metric Value']) / 1e3))
         fw = [o[4] for o in out if 'lean' in o[1]]
         bw = [o[4] for o in out if 'gather' in o[1]]
-        with open(os.path.join(P, "r01_ncu_launch_list_summary.txt"), "w") as f:
+        with open(os.path.join(P, f"{tag}_ncu_launch_list_summary.txt"), "w") as f:
             f.write("# ncu --metrics gpu__time_duration.sum --clock-control none; python bench.py --steps 3 --warmup 3 "
                     "--no-e2e --no-cpu (batch 64, bf16)\n# cold-cache serialised per-launch times: compare SHARES. "
                     "id, kernel, grid, block, us\n")
@@ -75,11 +83,11 @@ def main():
                 f.write(f"{o[0]:>3s}  {o[1]:72s} {o[2]:>14s} {o[3]:>14s} {o[4]:10.1f}\n")
             if fw and bw:
                 tf, tb = sum(fw) / len(fw), sum(bw) / len(bw)
-                bench = json.load(open(os.path.join(P, "r01_bench_bf16.json")))["kernels"]
+                bench = json.load(open(os.path.join(P, f"{tag}_bench_bf16.json")))["kernels"]
                 share = bench["backward_ms"] / (bench["backward_ms"] + bench["forward_ms"]) * 100
                 f.write(f"# mean forward {tf:.1f} us, mean backward {tb:.1f} us -> backward share of a step "
                         f"{tb / (tf + tb) * 100:.1f}% (bench.py CUDA events: {share:.1f}%)\n")
-        print(open(os.path.join(P, "r01_ncu_launch_list_summary.txt")).read().splitlines()[-1])
+        print(open(os.path.join(P, f"{tag}_ncu_launch_list_summary.txt")).read().splitlines()[-1])
 
 
 if __name__ == "__main__":
