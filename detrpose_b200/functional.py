@@ -135,14 +135,19 @@ class _HubToken(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hub, *value):
-        ctx.hub = hub
+        # weak: hub -> token -> this node -> hub would be a reference cycle, and the pyramid / gradient buffer
+        # of every pass would wait for the cycle collector instead of being freed with the graph.  The hub is
+        # kept alive by the core nodes of the same graph, which run before this node does.
+        ctx.hub_ref = weakref.ref(hub)
         ctx.n = len(value)
         return torch.zeros(1, dtype=torch.float32, device=value[0].device)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, _):
-        hub = ctx.hub
+        hub = ctx.hub_ref()
+        if hub is None:
+            return (None,) * (1 + ctx.n)
         gv, hub.buffer = hub.buffer, None
         hub.spent = True                       # a later forward on the same value starts a new hub
         if gv is None:

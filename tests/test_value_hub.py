@@ -145,3 +145,32 @@ def test_no_grad_forward_then_grad_forward_on_same_list():
     (o1 * go).sum().backward()
     ref = _reference_grad(w, memory, layers)
     assert rel_err(mem.grad.cpu().numpy(), ref.cpu().numpy()) <= TOL
+
+
+def test_no_device_memory_is_held_by_reference_cycles():
+    """Pyramid, gradient buffer and token of a pass are freed with its graph (no wait for the cycle collector):
+    the allocated device memory does not grow over repeated steps, with and without a backward pass."""
+    import gc
+    w, memory, layers = _stack_inputs(1, N=4, Lq=300)
+    loc, att, go = layers[0]
+    gc.collect()
+    gc.disable()
+    try:
+        def step(backward):
+            mem = memory.clone().requires_grad_(True)
+            value = otorch.make_value_list(mem, w["H"], w["shapes"])          # N > 1: a repacked pyramid per step
+            out = dp.ms_deform_attn_core(value, w["shapes"], loc, att)
+            if backward:
+                out.backward(go)
+        for backward in (True, False):
+            for _ in range(3):
+                step(backward)
+            torch.cuda.synchronize()
+            base = torch.cuda.memory_allocated()
+            for _ in range(10):
+                step(backward)
+            torch.cuda.synchronize()
+            grown = torch.cuda.memory_allocated() - base
+            assert grown <= memory.numel() * 4, (backward, grown)    # at most the one cached entry
+    finally:
+        gc.enable()
