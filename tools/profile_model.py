@@ -44,7 +44,7 @@ def group_of(name: str) -> str:
     return "elementwise/copy/other"
 
 
-def build_step(leg, dev, world):
+def build_step(leg, dev, world, sync_bn=True, static_graph=False):
     import torch.distributed as dist
     from torch.nn.parallel import DistributedDataParallel as DDP
     if leg == "train_l":
@@ -52,8 +52,13 @@ def build_step(leg, dev, world):
         criterion = rh.build_criterion().to(dev).train()
         net = model
         if world > 1:
-            model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
-            net = DDP(model, device_ids=[dev.index], output_device=dev.index, find_unused_parameters=True)
+            if sync_bn:                                   # src/misc/dist_utils.py:122 (sync_bn: True in the configs)
+                model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            if static_graph:                              # what-if: not what the reference does (:126)
+                net = DDP(model, device_ids=[dev.index], output_device=dev.index, static_graph=True,
+                          gradient_as_bucket_view=True)
+            else:
+                net = DDP(model, device_ids=[dev.index], output_device=dev.index, find_unused_parameters=True)
         params = [p for p in model.parameters() if p.requires_grad]
         opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-4)
         host = torch.rand(16, 3, 640, 640).pin_memory()
@@ -86,6 +91,9 @@ def main():
     ap.add_argument("--leg", default="train_l", choices=["train_l", "infer_s", "infer_x"])
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--arms", default="reference,b200")
+    ap.add_argument("--no-syncbn", action="store_true", help="what-if: plain BatchNorm under DDP (the reference converts to SyncBN)")
+    ap.add_argument("--static-graph", action="store_true", help="what-if: DDP(static_graph=True, gradient_as_bucket_view=True)")
+    ap.add_argument("--no-profiler", action="store_true", help="time only (CUDA events), no torch.profiler")
     args = ap.parse_args()
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -102,7 +110,7 @@ def main():
             rh.install_kernels()
         old, sys.stdout = sys.stdout, devnull
         try:
-            step, batch = build_step(args.leg, dev, world)
+            step, batch = build_step(args.leg, dev, world, sync_bn=not args.no_syncbn, static_graph=args.static_graph)
         finally:
             sys.stdout = old
         for _ in range(3):
@@ -110,6 +118,25 @@ def main():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
+        if args.no_profiler:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / args.steps
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            if rank == 0:
+                print(json.dumps({"leg": args.leg, "arm": arm, "n_gpus": world, "batch_per_gpu": batch,
+                                  "sync_bn": not args.no_syncbn, "static_graph": args.static_graph,
+                                  "ms_per_step": round(ms, 2), "img_per_s": round(batch * world / ms * 1e3, 1)}), flush=True)
+            del step
+            torch.cuda.empty_cache()
+            continue
         with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
             t0 = time.perf_counter()
             for _ in range(args.steps):
