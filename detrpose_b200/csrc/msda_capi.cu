@@ -45,6 +45,9 @@ int make_problem(msda::Problem& pb, int N, int Lq, int H, int Dh, int L, int P,
         return fail(MSDA_ERR_SHAPE, "unknown coord_mode %d", coord_mode);
     pb.N = N; pb.Lq = Lq; pb.H = H; pb.Dh = Dh; pb.L = L; pb.P = P;
     pb.coord_mode = coord_mode;
+    pb.magic_lp = msda::div_magic((uint32_t)(L * P));
+    pb.magic_p = msda::div_magic((uint32_t)P);
+    pb.magic_h = msda::div_magic((uint32_t)H);
     int64_t acc = 0;
     for (int l = 0; l < MSDA_MAX_LEVELS; ++l) {
         if (l < L) {
@@ -133,7 +136,10 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
     if (!aligned16(out) || !aligned16(locations) || !aligned16(attention))
         return fail(MSDA_ERR_ALIGN, "locations / attention / out must be 16-byte aligned");
     // variant 1 (default when the shape fits): lean kernel; variant 0: flat kernel
-    const int variant = g_fwd_variant.load();
+    // 100 + v: variant v without the streaming L2 prefetch of the pyramid (150: the automatic choice without it)
+    const int raw_variant = g_fwd_variant.load();
+    const int l2_prefetch = raw_variant >= 100 ? 0 : 1;
+    const int variant = raw_variant >= 100 ? (raw_variant == 150 ? -1 : raw_variant - 100) : raw_variant;
     const bool vbf = value_dtype == MSDA_BF16;
     const bool can_lean = msda::forward_lean_supported(pb, vbf);
     if (variant == 1 && !can_lean) return fail(MSDA_ERR_SHAPE, "lean forward does not support this shape");
@@ -145,11 +151,10 @@ MSDA_API int msda_b200_forward(const void* value, int value_dtype, const int64_t
         e = msda::forward_staged(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, small,
                                  (cudaStream_t)stream);
     } else {
-        // variants 4 / 5: the lean kernel compiled for 5 / 6 resident CTAs per SM (48 / 39 registers)
-        const int min_blocks = variant == 4 ? 5 : variant == 5 ? 6 : 4;
+        // variant 7: the one-lane-group form also for rows of at most 32 bytes (default there: two lane groups)
         e = (can_lean && variant != 0)
-            ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, min_blocks,
-                                 (cudaStream_t)stream)
+            ? msda::forward_lean(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16,
+                                 (cudaStream_t)stream, nullptr, 1, nullptr, variant == 7 ? 0 : -1, l2_prefetch)
             : msda::forward_flat(pb, value, vbf, locations, attention, out, out_dtype == MSDA_BF16, (cudaStream_t)stream);
     }
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward launch");
@@ -230,7 +235,7 @@ MSDA_API int msda_b200_forward_fused(const void* value, int value_dtype, const i
         return fail(MSDA_ERR_ALIGN, "fused forward: offsets / logits / out / attention_out must be 16-byte, ref_points 8-byte aligned");
     const bool vbf = value_dtype == MSDA_BF16;
     if (!msda::forward_lean_supported(pb, vbf)) return fail(MSDA_ERR_SHAPE, "fused forward does not support this shape");
-    const cudaError_t e = msda::forward_lean(pb, value, vbf, offsets, logits, out, out_dtype == MSDA_BF16, 4,
+    const cudaError_t e = msda::forward_lean(pb, value, vbf, offsets, logits, out, out_dtype == MSDA_BF16,
                                              (cudaStream_t)stream, ref_points, ref_levels, attention_out);
     return e == cudaSuccess ? MSDA_OK : cuda_fail(e, "msda_b200_forward_fused launch");
 }

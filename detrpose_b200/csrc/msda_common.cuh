@@ -30,8 +30,14 @@ struct Problem {
     int32_t S;                        // sum_l h*w
     int64_t vs_n, vs_s, vs_h;         // value strides in elements (channel stride 1)
     int32_t coord_mode;
+    uint32_t magic_lp, magic_p, magic_h;   // ceil(2^32 / d) for d = L*P, P, H: see fastdiv
     LevelGeom geom;
 };
+
+// n / d for n * d < 2^32 with magic = ceil(2^32 / d) (host: div_magic): one IMAD.HI instead of the ~20
+// instructions of a 32-bit division by a run-time value
+__host__ __device__ inline uint32_t div_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((0x100000000ULL + d - 1) / d); }
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t magic) { return magic ? __umulhi(n, magic) : n; }
 
 __device__ __forceinline__ float pixel_coord(float loc, float size, int coord_mode) {
     // every op explicitly rounded so that nvcc cannot contract across them

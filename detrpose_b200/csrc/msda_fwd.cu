@@ -137,18 +137,99 @@ struct FusedPrologue {
     float* attn_out;        // (N, Lq, H, L, P) or nullptr
 };
 
-template <int G, int K, bool VBF, bool OBF, int MINB>
-__global__ void __launch_bounds__(kFwdThreads, MINB)
+// acc[0 .. E/2) += row * w for one 16-byte piece of a channel row (float2 accumulators, FFMA2)
+template <bool VBF>
+__device__ __forceinline__ void fma_row(const uint4& r, const float w, float2* acc) {
+    constexpr int P2 = Vec<VBF>::kElems / 2;
+    const float2 ww = make_float2(w, w);
+    float2 f[P2];
+    if constexpr (VBF) {
+        f[0] = make_float2(bf16_lo(r.x), bf16_hi(r.x));
+        f[1] = make_float2(bf16_lo(r.y), bf16_hi(r.y));
+        f[2] = make_float2(bf16_lo(r.z), bf16_hi(r.z));
+        f[3] = make_float2(bf16_lo(r.w), bf16_hi(r.w));
+    } else {
+        f[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
+        f[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
+    }
+#pragma unroll
+    for (int e2 = 0; e2 < P2; ++e2) acc[e2] = __ffma2_rn(f[e2], ww, acc[e2]);
+}
+
+// N2 float2 (2 * N2 consecutive channels) -> out, with the widest stores the count allows
+template <bool OBF, int N2>
+__device__ __forceinline__ void store_out(char* o, const float2* a) {
+    if constexpr (OBF) {
+        if constexpr (N2 % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < N2; i += 4)
+                *reinterpret_cast<uint4*>(o + i * 4) =
+                    make_uint4(pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i + 1].x, a[i + 1].y),
+                               pack_bf16x2(a[i + 2].x, a[i + 2].y), pack_bf16x2(a[i + 3].x, a[i + 3].y));
+        } else if constexpr (N2 % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < N2; i += 2)
+                *reinterpret_cast<uint2*>(o + i * 4) =
+                    make_uint2(pack_bf16x2(a[i].x, a[i].y), pack_bf16x2(a[i + 1].x, a[i + 1].y));
+        } else {
+#pragma unroll
+            for (int i = 0; i < N2; ++i) *reinterpret_cast<uint32_t*>(o + i * 4) = pack_bf16x2(a[i].x, a[i].y);
+        }
+    } else {
+        if constexpr (N2 % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < N2; i += 2)
+                *reinterpret_cast<float4*>(o + i * 8) = make_float4(a[i].x, a[i].y, a[i + 1].x, a[i + 1].y);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N2; ++i) *reinterpret_cast<float2*>(o + i * 8) = a[i];
+        }
+    }
+}
+
+// PAIR (K == 1, rows of at most 32 bytes): 2*G lanes per item, the lower G take the two x0 corners of a sample
+// and the upper G the two x1 corners; the two halves are summed by one shuffle per accumulator at the end and
+// each half stores half of the item's output vector.  With one or two lanes per item a warp carries 32 or 16
+// items and every thread waits on its own chain of loads: DETRPose-N (Dh 16, bf16) runs 188 -> 118 us at batch 64
+// this way (97 us on a head-major pyramid, where the x0 / x1 rows are one contiguous request).
+// Streaming L2 prefetch of the pyramid.  The gather reads every pyramid byte about six times, but the FIRST touch
+// of a row is a random 64-byte DRAM read (35 % of the sectors miss L2: a batch of pyramids is larger than L2).
+// Each CTA therefore asks L2, with one bulk-prefetch instruction, for the contiguous slice of the pyramid that
+// the CTAs `ahead` positions later gather from: DRAM is read sequentially and a little ahead of time.  Worth 3 %
+// (140 -> 135 us); looking further ahead (one or more waves of CTAs) is slower than no prefetch at all.
+// bytes == 0: off (pyramid not one dense block).
+struct L2Prefetch {
+    int64_t bytes;          // whole pyramid, all images
+    uint32_t per_cta;       // slice per CTA (multiple of 16)
+    uint32_t ahead;         // in CTAs
+};
+
+template <int G, int K, bool VBF, bool OBF, bool PAIR>
+__global__ void __launch_bounds__(kFwdThreads, 4)
 fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 const float* __restrict__ loc, const float* __restrict__ attn,
-                char* __restrict__ out, const FusedPrologue fz) {
-    constexpr int E = Vec<VBF>::kElems;
+                char* __restrict__ out, const FusedPrologue fz, const L2Prefetch pf) {
+    constexpr int W = 16;                            // bytes per lane and corner row: one LDG.128
+    constexpr int E = Vec<VBF>::kElems;              // channels per lane vector
     constexpr int E2 = E / 2;
     constexpr int ES = VBF ? 2 : 4;
-    constexpr int IPC = kFwdThreads / G;             // items per CTA
+    static_assert(!PAIR || (K == 1 && G * W <= 64), "PAIR: one vector per lane, rows of at most 64 bytes");
+    constexpr int GG = PAIR ? 2 * G : G;             // lanes per item
+    constexpr int IPC = kFwdThreads / GG;            // items per CTA
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
+    if (pf.bytes != 0 && tid == 0) {
+        // the first `ahead` CTAs also fetch the slices nobody is ahead of
+        for (int64_t c = blockIdx.x < pf.ahead ? blockIdx.x : (int64_t)blockIdx.x + pf.ahead;
+             c <= (int64_t)blockIdx.x + pf.ahead; c += pf.ahead) {
+            const int64_t off = c * pf.per_cta;
+            if (off < pf.bytes) {
+                const uint32_t len = (uint32_t)min((int64_t)pf.per_cta, pf.bytes - off);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(value + off), "r"(len) : "memory");
+            }
+        }
+    }
     const int LP = pb.L * pb.P;
     const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
     const int64_t item0 = (int64_t)blockIdx.x * IPC;
@@ -177,8 +258,9 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
         const int nsamp = nitems * LP;
         const float2* lsrc = reinterpret_cast<const float2*>(loc) + item0 * LP;
         const float* asrc = attn + item0 * LP;
-        int il = tid / LP, sl = tid - il * LP;       // item inside the CTA, sample inside the item
-        const int dil = kFwdThreads / LP, dsl = kFwdThreads - dil * LP;
+        // item inside the CTA, sample inside the item (tid, kFwdThreads < 2^32 / LP: fastdiv is exact)
+        int il = (int)fastdiv((uint32_t)tid, pb.magic_lp), sl = tid - il * LP;
+        const int dil = (int)fastdiv((uint32_t)kFwdThreads, pb.magic_lp), dsl = kFwdThreads - dil * LP;
         // the loads of up to three samples are issued before the first dependent instruction: one exposed
         // DRAM latency per batch instead of one per sample (a thread has 3 samples for G = 4, 6 for G = 2)
         constexpr int PF = 3;
@@ -196,7 +278,7 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 if (s0 + u * kFwdThreads >= nsamp) break;
                 float2 xy = xy_[u];
                 float a = a_[u];
-                const int l = sl / pb.P;
+                const int l = (int)fastdiv((uint32_t)sl, pb.magic_p);
                 const int Hl = pb.geom.h[l], Wl = pb.geom.w[l];
                 if (fused) {
                     const float2 st = stat_s[il];
@@ -212,15 +294,23 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
                 const int yc0 = min(max(sm.y0, 0), Hl - 1), yc1 = min(max(sm.y0 + 1, 0), Hl - 1);
                 const uint32_t r0 = (uint32_t)(pb.geom.start[l] + yc0 * Wl), r1 = (uint32_t)(pb.geom.start[l] + yc1 * Wl);
                 unsigned char* dst = smem_raw + il * item_stride + sl * 32;
-                reinterpret_cast<float4*>(dst)[0] = make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
+                // PAIR keeps the two corners of one x side next to each other: {nw, sw, ne, se}
+                reinterpret_cast<float4*>(dst)[0] = PAIR ? make_float4(sm.w_nw * a, sm.w_sw * a, sm.w_ne * a, sm.w_se * a)
+                                                         : make_float4(sm.w_nw * a, sm.w_ne * a, sm.w_sw * a, sm.w_se * a);
                 // A corner outside the map keeps an exact zero weight and points at the clamped pixel, which is
                 // a VALID corner of the same sample whenever the sample touches the map at all (so the result,
                 // Inf/NaN propagation included, is what per-corner dropping gives); a sample with no valid
                 // corner is flagged and skipped as a whole.  One predicate per sample instead of one per corner.
                 const bool any = (sm.vx0 | sm.vx1) & (sm.vy0 | sm.vy1);
-                reinterpret_cast<uint4*>(dst)[1] = make_uint4(any ? (r0 + xc0) * row_bytes : 0xffffffffu,
-                                                              (r0 + xc1) * row_bytes, (r1 + xc0) * row_bytes,
-                                                              (r1 + xc1) * row_bytes);
+                if constexpr (PAIR)
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(any ? (r0 + xc0) * row_bytes : 0xffffffffu,
+                                                                  (r1 + xc0) * row_bytes,
+                                                                  any ? (r0 + xc1) * row_bytes : 0xffffffffu,
+                                                                  (r1 + xc1) * row_bytes);
+                else
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(any ? (r0 + xc0) * row_bytes : 0xffffffffu,
+                                                                  (r0 + xc1) * row_bytes, (r1 + xc0) * row_bytes,
+                                                                  (r1 + xc1) * row_bytes);
                 il += dil; sl += dsl;
                 if (sl >= LP) { sl -= LP; ++il; }
             }
@@ -228,19 +318,26 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     }
     __syncthreads();
 
-    // ---- phase 2: G lanes per item gather and accumulate ----
+    // ---- phase 2: G lanes per item (PAIR: per x side of an item) gather and accumulate ----
     const int lane = tid % G;
-    const int il = tid / G;
-    // rows that are not a power-of-two number of 16-byte vectors (Dh = 48 bf16: 6) use the next power of
+    const bool active = tid / GG < nitems;
+    const int il = active ? tid / GG : 0;            // surplus threads shadow item 0 (no early exit: PAIR shuffles)
+    const int half = PAIR ? (tid / G) & 1 : 0;
+    // rows that are not a power-of-two number of W-byte vectors (Dh = 48 bf16: 96 bytes) use the next power of
     // two of lanes with the surplus lanes idle: one request per corner row instead of three
-    if (il >= nitems || lane * 16 >= pb.Dh * ES) return;
+    if (!PAIR && (!active || lane * W >= pb.Dh * ES)) return;
     const int64_t item = item0 + il;
-    // 32-bit division whenever the item index fits (a 64-bit divide is a ~100-instruction subroutine per thread)
+    // (n, h) of the item: the CTA's first item is divided once (CTA-uniform, 64-bit safe), the item inside the
+    // CTA adds at most IPC to its head index: one IMAD.HI per thread instead of two run-time divisions
     int h, n;
     if (items <= 0x7fffffffLL) {
-        const unsigned it = (unsigned)item;
-        h = (int)(it % (unsigned)pb.H);
-        n = (int)(it / ((unsigned)pb.H * (unsigned)pb.Lq));
+        const uint32_t nq0 = (uint32_t)item0 / (uint32_t)pb.H;                 // CTA-uniform
+        const uint32_t n0 = nq0 / (uint32_t)pb.Lq, q0 = nq0 - n0 * (uint32_t)pb.Lq;
+        const uint32_t hh = ((uint32_t)item0 - nq0 * (uint32_t)pb.H) + (uint32_t)il;
+        const uint32_t dq = fastdiv(hh, pb.magic_h);
+        h = (int)(hh - dq * (uint32_t)pb.H);
+        const uint32_t qq = q0 + dq;                                           // dq <= IPC
+        n = (int)(pb.Lq >= IPC ? n0 + (qq >= (uint32_t)pb.Lq) : n0 + qq / (uint32_t)pb.Lq);
     } else {
         h = (int)(item % pb.H);
         n = (int)(item / ((int64_t)pb.H * pb.Lq));
@@ -252,76 +349,99 @@ fwd_lean_kernel(const Problem pb, const char* __restrict__ value,
     for (int c = 0; c < K * E2; ++c) acc[c] = make_float2(0.0f, 0.0f);
 
     const unsigned char* ip = smem_raw + il * item_stride;
-    // B samples per step: all of their 4*K*B row loads are issued before the first use, so that every
-    // thread keeps 8 (K == 1) independent 16-byte loads in flight -- the kernel is latency-bound otherwise
-    constexpr int B = K == 1 ? 2 : 1;
-    for (int s = 0; s < LP; s += B) {
-        float wv[B][4];
-        uint4 raw[B][K][4];
-        bool live[B];
+    constexpr int OS = OBF ? 2 : 4;
+    if constexpr (PAIR) {
+        // four samples per step: 128 bytes of independent loads in flight per thread, as in the unpaired loop
+        constexpr int B = 4;
+        const unsigned char* hp = ip + half * 8;
+        for (int s = 0; s < LP; s += B) {
+            float2 wv[B];
+            uint4 raw[B][2];
+            bool live[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-            const bool in = s + b < LP;                                  // odd tail: re-reads the previous entry
-            const unsigned char* e = ip + (in ? s + b : s) * 32;
-            const float4 w = reinterpret_cast<const float4*>(e)[0];
-            const uint4 o = reinterpret_cast<const uint4*>(e)[1];
-            wv[b][0] = w.x; wv[b][1] = w.y; wv[b][2] = w.z; wv[b][3] = w.w;
-            live[b] = in && o.x != 0xffffffffu;                          // sample with at least one valid corner
-            const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
-            if (live[b]) {
+            for (int b = 0; b < B; ++b) {
+                const bool in = s + b < LP;
+                const unsigned char* e = hp + (in ? s + b : s) * 32;
+                wv[b] = *reinterpret_cast<const float2*>(e);
+                const uint2 o = *reinterpret_cast<const uint2*>(e + 16);
+                live[b] = in && o.x != 0xffffffffu;
+                if (live[b]) {
+                    raw[b][0] = ldg_nc_v4(vbase + o.x);
+                    raw[b][1] = ldg_nc_v4(vbase + o.y);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                if (!live[b]) continue;
+                fma_row<VBF>(raw[b][0], wv[b].x, acc);
+                fma_row<VBF>(raw[b][1], wv[b].y, acc);
+            }
+        }
+        // x0 side + x1 side; afterwards each side stores its half of the lane's E channels
+#pragma unroll
+        for (int e2 = 0; e2 < E2; ++e2) {
+            acc[e2].x += __shfl_xor_sync(0xffffffffu, acc[e2].x, G);
+            acc[e2].y += __shfl_xor_sync(0xffffffffu, acc[e2].y, G);
+        }
+        if (!active) return;
+        constexpr int HE2 = E2 / 2;
+        float2 mine[HE2];
+#pragma unroll
+        for (int e2 = 0; e2 < HE2; ++e2) mine[e2] = half ? acc[HE2 + e2] : acc[e2];
+        store_out<OBF, HE2>(out + (item * pb.Dh + lane * E + half * (E / 2)) * OS, mine);
+        return;
+    } else {
+        // B samples per step: all of their 4*K*B row loads are issued before the first use, so that every
+        // thread keeps 128 bytes of independent loads in flight -- the kernel is latency-bound otherwise
+        constexpr int B = K == 1 ? 2 : 1;
+        for (int s = 0; s < LP; s += B) {
+            float wv[B][4];
+            uint4 raw[B][K][4];
+            bool live[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const bool in = s + b < LP;                                  // odd tail: re-reads the previous entry
+                const unsigned char* e = ip + (in ? s + b : s) * 32;
+                const float4 w = reinterpret_cast<const float4*>(e)[0];
+                const uint4 o = reinterpret_cast<const uint4*>(e)[1];
+                wv[b][0] = w.x; wv[b][1] = w.y; wv[b][2] = w.z; wv[b][3] = w.w;
+                live[b] = in && o.x != 0xffffffffu;                          // sample with at least one valid corner
+                const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                if (live[b]) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) raw[b][k][c] = ldg_nc_v4(vbase + ov[c] + k * G * W);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                if (!live[b]) continue;
 #pragma unroll
                 for (int k = 0; k < K; ++k)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) raw[b][k][c] = ldg_nc_v4(vbase + ov[c] + k * G * 16);
+                    for (int c = 0; c < 4; ++c) fma_row<VBF>(raw[b][k][c], wv[b][c], acc + k * E2);
             }
         }
+        char* obase = out + (item * pb.Dh + lane * E) * OS;
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-            if (!live[b]) continue;
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float2 f[E2];
-                    const uint4 r = raw[b][k][c];
-                    if constexpr (VBF) {
-                        f[0] = make_float2(bf16_lo(r.x), bf16_hi(r.x));
-                        f[1] = make_float2(bf16_lo(r.y), bf16_hi(r.y));
-                        f[2] = make_float2(bf16_lo(r.z), bf16_hi(r.z));
-                        f[3] = make_float2(bf16_lo(r.w), bf16_hi(r.w));
-                    } else {
-                        f[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
-                        f[1] = make_float2(__uint_as_float(r.z), __uint_as_float(r.w));
-                    }
-                    const float2 ww = make_float2(wv[b][c], wv[b][c]);
-#pragma unroll
-                    for (int e2 = 0; e2 < E2; ++e2) acc[k * E2 + e2] = __ffma2_rn(f[e2], ww, acc[k * E2 + e2]);
-                }
-        }
+        for (int k = 0; k < K; ++k) store_out<OBF, E2>(obase + k * G * E * OS, acc + k * E2);
     }
+}
 
-    constexpr int OS = OBF ? 2 : 4;
-    char* obase = out + (item * pb.Dh + lane * E) * OS;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        char* o = obase + k * G * E * OS;
-        const float2* a2 = acc + k * E2;
-        if constexpr (OBF) {
-            if constexpr (E == 8) {
-                uint4 v;
-                v.x = pack_bf16x2(a2[0].x, a2[0].y); v.y = pack_bf16x2(a2[1].x, a2[1].y);
-                v.z = pack_bf16x2(a2[2].x, a2[2].y); v.w = pack_bf16x2(a2[3].x, a2[3].y);
-                *reinterpret_cast<uint4*>(o) = v;
-            } else {
-                uint2 v;
-                v.x = pack_bf16x2(a2[0].x, a2[0].y); v.y = pack_bf16x2(a2[1].x, a2[1].y);
-                *reinterpret_cast<uint2*>(o) = v;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < E2; e += 2)
-                *reinterpret_cast<float4*>(o + e * 8) = make_float4(a2[e].x, a2[e].y, a2[e + 1].x, a2[e + 1].y);
-        }
+// lanes per item of the lean kernel for a channel row of nv 16-byte vectors
+struct LeanShape { int g, k; };
+static LeanShape lean_shape(int nv) {
+    switch (nv) {
+        case 1: return {1, 1};
+        case 2: return {2, 1};
+        case 3: return {1, 3};
+        case 4: return {4, 1};
+        case 6: return {8, 1};
+        case 8: return {8, 1};
+        case 12: return {4, 3};
+        case 16: return {8, 2};
+        default: return {0, 0};
     }
 }
 
@@ -329,60 +449,79 @@ static size_t lean_smem(const Problem& pb, int ipc) {
     return (size_t)ipc * (pb.L * pb.P * sizeof(SampleParams) + 16 + sizeof(float2));
 }
 
-template <int G, int K, bool VBF>
+template <int G, int K, bool VBF, bool PAIR>
 static cudaError_t launch_lean(const Problem& pb, const void* value, const float* loc, const float* attn,
-                               void* out, bool out_bf16, int min_blocks, const FusedPrologue& fz, cudaStream_t st) {
-    constexpr int IPC = kFwdThreads / G;
+                               void* out, bool out_bf16, const FusedPrologue& fz, bool l2_prefetch, cudaStream_t st) {
+    constexpr int IPC = kFwdThreads / (PAIR ? 2 * G : G);
     const int64_t items = (int64_t)pb.N * pb.Lq * pb.H;
     const unsigned grid = (unsigned)((items + IPC - 1) / IPC);
     const size_t smem = lean_smem(pb, IPC);
+    // L2 prefetch: only when the pyramid is one dense channel-last block (N, S, H, Dh), a quarter wave ahead
+    L2Prefetch pf{0, 0, 0};
+    {
+        const int es = VBF ? 2 : 4;
+        const int64_t img = (int64_t)pb.S * pb.H * pb.Dh;
+        const bool pm = pb.vs_h == pb.Dh && pb.vs_s == (int64_t)pb.H * pb.Dh;
+        if (l2_prefetch && pm && pb.vs_n == img && grid > 0) {
+            int sms = 148, dev = 0;
+            if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            pf.bytes = img * pb.N * es;
+            pf.per_cta = (uint32_t)(((pf.bytes + grid - 1) / grid + 15) / 16 * 16);
+            pf.ahead = (uint32_t)max(1, sms / 4);
+        }
+    }
     auto launch = [&](auto kern) -> cudaError_t {
         if (smem > 48 * 1024) {
             const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out, fz);
+        kern<<<grid, kFwdThreads, smem, st>>>(pb, (const char*)value, loc, attn, (char*)out, fz, pf);
         return cudaGetLastError();
     };
-    // min_blocks: occupancy target (registers per thread are capped accordingly); K == 1 only
-    if (K == 1 && min_blocks == 6)
-        return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 6>) : launch(fwd_lean_kernel<G, K, VBF, false, 6>);
-    if (K == 1 && min_blocks == 5)
-        return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 5>) : launch(fwd_lean_kernel<G, K, VBF, false, 5>);
-    return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, 4>) : launch(fwd_lean_kernel<G, K, VBF, false, 4>);
+    return out_bf16 ? launch(fwd_lean_kernel<G, K, VBF, true, PAIR>) : launch(fwd_lean_kernel<G, K, VBF, false, PAIR>);
 }
 
 // The lean kernel needs 32-bit row offsets and its parameter table in shared memory.
 bool forward_lean_supported(const Problem& pb, bool value_bf16) {
     const int es = value_bf16 ? 2 : 4;
     const int nv = pb.Dh * es / 16;
-    if (!(nv == 1 || nv == 2 || nv == 3 || nv == 4 || nv == 6 || nv == 8 || nv == 12 || nv == 16)) return false;
+    const int g = lean_shape(nv).g;
+    if (g == 0) return false;
     if ((int64_t)pb.S * pb.vs_s * es >= (int64_t)0x7fffffff) return false;
-    const int g = nv == 3 ? 1 : nv == 6 ? 8 : nv == 12 ? 4 : nv == 16 ? 8 : nv;
     return lean_smem(pb, kFwdThreads / g) <= 96 * 1024;
 }
 
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st,
-                         const float* ref, int ref_levels, float* attn_out) {
+                         const float* attn, void* out, bool out_bf16, cudaStream_t st,
+                         const float* ref, int ref_levels, float* attn_out, int pair_mode, int l2_prefetch) {
     const int nv = pb.Dh * (value_bf16 ? 2 : 4) / 16;
     const FusedPrologue fz{ref, ref_levels, attn_out};
-#define MSDA_LEAN_CASE(NV, G, K)                                                          \
-    case NV:                                                                              \
-        return value_bf16 ? launch_lean<G, K, true>(pb, value, loc, attn, out, out_bf16, min_blocks, fz, st)  \
-                          : launch_lean<G, K, false>(pb, value, loc, attn, out, out_bf16, min_blocks, fz, st);
+    const bool l2pf = l2_prefetch != 0;
+    // rows of 16 or 32 bytes: one or two lanes per item leave a warp with too few rows in flight per instruction
+    // stream; the paired form (two lanes groups per item) is the default there
+    const bool pair = nv <= 2 && pair_mode != 0;
+#define MSDA_LEAN(G, K, PAIR)                                                                                 \
+    return value_bf16 ? launch_lean<G, K, true, PAIR>(pb, value, loc, attn, out, out_bf16, fz, l2pf, st) \
+                      : launch_lean<G, K, false, PAIR>(pb, value, loc, attn, out, out_bf16, fz, l2pf, st)
+    if (pair) {       // 2 * G lanes per item
+        switch (nv) {
+            case 1: MSDA_LEAN(1, 1, true);
+            case 2: MSDA_LEAN(2, 1, true);
+            default: break;
+        }
+    }
     switch (nv) {
-        MSDA_LEAN_CASE(1, 1, 1)
-        MSDA_LEAN_CASE(2, 2, 1)
-        MSDA_LEAN_CASE(3, 1, 3)
-        MSDA_LEAN_CASE(4, 4, 1)
-        MSDA_LEAN_CASE(6, 8, 1)
-        MSDA_LEAN_CASE(8, 8, 1)
-        MSDA_LEAN_CASE(12, 4, 3)
-        MSDA_LEAN_CASE(16, 8, 2)
+        case 1: MSDA_LEAN(1, 1, false);
+        case 2: MSDA_LEAN(2, 1, false);
+        case 3: MSDA_LEAN(1, 3, false);
+        case 4: MSDA_LEAN(4, 1, false);
+        case 6: MSDA_LEAN(8, 1, false);
+        case 8: MSDA_LEAN(8, 1, false);
+        case 12: MSDA_LEAN(4, 3, false);
+        case 16: MSDA_LEAN(8, 2, false);
         default: return cudaErrorInvalidValue;
     }
-#undef MSDA_LEAN_CASE
+#undef MSDA_LEAN
 }
 
 template <int G, int K, bool VBF>

@@ -15,8 +15,10 @@ cudaError_t forward_flat(const Problem& pb, const void* value, bool value_bf16, 
 bool forward_lean_supported(const Problem& pb, bool value_bf16);
 // ref != nullptr: fused prologue -- loc = sampling offsets, attn = attention logits (see msda_fwd.cu)
 cudaError_t forward_lean(const Problem& pb, const void* value, bool value_bf16, const float* loc,
-                         const float* attn, void* out, bool out_bf16, int min_blocks, cudaStream_t st,
-                         const float* ref = nullptr, int ref_levels = 1, float* attn_out = nullptr);
+                         const float* attn, void* out, bool out_bf16, cudaStream_t st,
+                         const float* ref = nullptr, int ref_levels = 1, float* attn_out = nullptr,
+                         int pair_mode = -1,        // two lane groups per item (rows <= 32 bytes): -1 auto, 0 off
+                         int l2_prefetch = 1);      // streaming L2 prefetch of the pyramid ahead of the gathers
 
 // msda_fwd_staged.cu
 bool forward_staged_supported(const Problem& pb, bool value_bf16, bool small);

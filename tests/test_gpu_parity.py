@@ -67,11 +67,12 @@ def _arbiter(case, memory=None, grad_out=None):
     return out, gm, gl, ga
 
 
-@pytest.fixture(params=[(1, 1), (0, 0), (2, 1), (3, 2)],
-                ids=["lean+gather", "flat+flat", "staged+gather", "staged_small+gather512"])
+@pytest.fixture(params=[(1, 1), (0, 0), (2, 1), (3, 2), (107, 1)],
+                ids=["lean+gather", "flat+flat", "staged+gather", "staged_small+gather512", "lean_plain+gather"])
 def bwd_variant(request):
     """Run under every kernel variant.  Forward: 1 = lean (default), 0 = flat, 2 / 3 = TMA-staged coarse
-    levels (one big CTA per SM / small CTAs); backward: 1 = gather form (default when the shape fits),
+    levels (one big CTA per SM / small CTAs), 107 = lean without its two defaults (one lane group per item
+    also for rows of at most 32 bytes, no L2 prefetch); backward: 1 = gather form (default when the shape fits),
     2 = the same with 512 threads x 128 registers, 0 = flat + vector reductions.  A forced
     variant that does not support a shape fails loudly in the library; those combinations are skipped."""
     lib = _lib.load()
