@@ -96,7 +96,13 @@ MSDA_API const char* msda_b200_last_error(void);
 MSDA_API int msda_b200_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Tuning knob for benchmarks: pin the forward / backward kernel variant
- * (-1 = automatic selection, the default).  Process-wide, atomic. */
+ * (-1 = automatic selection, the default).  Process-wide, atomic.
+ * forward : 0 flat, 1 lean (the automatic choice when the shape fits), 2 / 3 TMA-staged coarse levels (one big
+ *           CTA per SM / small CTAs), 7 lean with one lane group per item also for rows of at most 32 bytes;
+ *           100 + v = variant v without the streaming L2 prefetch of the pyramid (150: automatic without it)
+ * backward: 0 flat (vector reductions), 1 gather form (automatic when the shape fits), 2 gather form with
+ *           512 threads x 128 registers
+ * A pinned variant that does not support a shape makes the call fail (MSDA_ERR_SHAPE), it never falls back. */
 MSDA_API int msda_b200_set_variant(int fwd_variant, int bwd_variant);
 
 /* Diagnostic: device buffer of 8 uint64 per backward CTA (N*H*L CTAs) that receives clock64()
