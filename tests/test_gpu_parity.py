@@ -579,3 +579,32 @@ def test_tiny_attention_weights(tiny, bwd_variant):
     # absolute worst case of the dropped contributions: below 1e-30 * |grad_out| * |value| per sample
     if abs(tiny) < 1e-30:
         assert np.abs(gl[mask] - a_gl[mask]).max() <= 1e-25
+
+
+@pytest.mark.parametrize("Dh,vdt", [(8, torch.bfloat16), (16, torch.bfloat16), (8, torch.float32), (16, torch.float32),
+                                    (32, torch.bfloat16)])
+def test_forward_forms_agree(Dh, vdt):
+    """The forms the lean forward chooses between (msda_fwd.cu): two lane groups per item for channel rows of
+    at most 32 bytes (the default there) against one (variant 107) and against the flat kernel (0), on an
+    item count that leaves the last CTA partly filled; and the L2 prefetch (a hint) changes no bit."""
+    from detrpose_b200 import functional as MF
+    lib = _lib.load()
+    H, P, shapes, N, Lq = 4, 6, ((13, 17), (7, 9)), 3, 77              # 924 items: not a multiple of 32 .. 256
+    inp = synthetic.make_inputs(N, Lq, H, Dh, shapes, P, seed=5, device=DEV, clip=(-0.3, 1.3), value_dtype=vdt)
+    pyr = MF.pack_value(inp["memory"], inp["shapes"], H)
+    loc, att = inp["locations"], inp["attention"]
+    cm = MF.get_default_coord_mode()
+    outs = {}
+    try:
+        for v in (-1, 150, 107, 0):
+            lib.msda_b200_set_variant(v, -1)
+            outs[v] = MF._forward_raw(pyr, inp["shapes"], loc, att, torch.float32, cm)
+    finally:
+        lib.msda_b200_set_variant(-1, -1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[-1], outs[150])
+    ref = otorch.core(otorch.make_value_list(inp["memory"].float(), H, shapes), shapes, loc, att)
+    for v in (-1, 107, 0):
+        assert rel_err(outs[v].cpu().numpy(), ref.cpu().numpy()) <= TOL, v
+    if Dh * (2 if vdt == torch.bfloat16 else 4) > 32:
+        assert torch.equal(outs[-1], outs[107])            # one form only for wider rows
