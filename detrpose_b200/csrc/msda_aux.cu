@@ -179,82 +179,112 @@ __device__ __forceinline__ uint4 floats_to_vec(const float* f) {
         return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
 }
 
-template <bool SBF, bool DBF>
+// U sub-tiles of 64 positions per block: a thread issues the loads of all of them before the first conversion,
+// so that 16 * U bytes per thread are in flight (one 16-byte load per thread and barrier left the copy bound by
+// latency: 3.5 TB/s at U = 1, tools/bench_repack.py).
+template <bool SBF, bool DBF, int U>
 __global__ void __launch_bounds__(256)
 repack_vec_kernel(const Problem pb, const LevelViews src, const TileMap64 tm, char* __restrict__ dst) {
-    extern __shared__ float tile[];                   // [Dh][65]
+    extern __shared__ float tile[];                   // [U][Dh][65]
     constexpr int VS = ElemVec<SBF>::n, VD = ElemVec<DBF>::n, PITCH = kVecTileS + 1;
     const int nh = blockIdx.y, n = nh / pb.H, h = nh % pb.H;
     int l = 0;
     while (l + 1 < pb.L && (int)blockIdx.x >= tm.first_tile[l + 1]) ++l;
-    const int s0 = ((int)blockIdx.x - tm.first_tile[l]) * kVecTileS;
+    const int s00 = ((int)blockIdx.x - tm.first_tile[l]) * (kVecTileS * U);
     const int hw = pb.geom.h[l] * pb.geom.w[l];
     const char* sp = reinterpret_cast<const char*>(src.ptr[l]);
     constexpr int SES = SBF ? 2 : 4, DES = DBF ? 2 : 4;
+    const int sub = pb.Dh * PITCH;                    // floats per sub-tile
     // load: channel rows, VS positions per 16-byte vector
     for (int idx = threadIdx.x; idx < pb.Dh * (kVecTileS / VS); idx += 256) {
         const int c = idx / (kVecTileS / VS), v = idx % (kVecTileS / VS);
-        const int s = s0 + v * VS;
-        float f[VS];
-        const int64_t e = (int64_t)nh * src.s_nh[l] + (int64_t)c * src.s_c[l] + s;
-        if (s + VS <= hw) {
-            vec_to_floats<SBF>(__ldg(reinterpret_cast<const uint4*>(sp + e * SES)), f);
-        } else {
+        const int64_t e0 = (int64_t)nh * src.s_nh[l] + (int64_t)c * src.s_c[l];
+        uint4 raw[U];
 #pragma unroll
-            for (int j = 0; j < VS; ++j) f[j] = (s + j < hw) ? load_elem<SBF>(sp, e + j) : 0.0f;
+        for (int u = 0; u < U; ++u) {
+            const int s = s00 + u * kVecTileS + v * VS;
+            if (s + VS <= hw) raw[u] = __ldg(reinterpret_cast<const uint4*>(sp + (e0 + s) * SES));
         }
 #pragma unroll
-        for (int j = 0; j < VS; ++j) tile[c * PITCH + v * VS + j] = f[j];
+        for (int u = 0; u < U; ++u) {
+            const int s = s00 + u * kVecTileS + v * VS;
+            float f[VS];
+            if (s + VS <= hw) {
+                vec_to_floats<SBF>(raw[u], f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VS; ++j) f[j] = (s + j < hw) ? load_elem<SBF>(sp, e0 + s + j) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < VS; ++j) tile[u * sub + c * PITCH + v * VS + j] = f[j];
+        }
     }
     __syncthreads();
     // store: position rows, VD channels per 16-byte vector
     const int64_t drow = (int64_t)pb.H * pb.Dh;
     for (int idx = threadIdx.x; idx < kVecTileS * (pb.Dh / VD); idx += 256) {
         const int p = idx / (pb.Dh / VD), cv = idx % (pb.Dh / VD);
-        if (s0 + p >= hw) continue;
-        float f[VD];
 #pragma unroll
-        for (int j = 0; j < VD; ++j) f[j] = tile[(cv * VD + j) * PITCH + p];
-        const int64_t d = ((int64_t)n * pb.S + pb.geom.start[l] + s0 + p) * drow + (int64_t)h * pb.Dh + cv * VD;
-        *reinterpret_cast<uint4*>(dst + d * DES) = floats_to_vec<DBF>(f);
+        for (int u = 0; u < U; ++u) {
+            const int s = s00 + u * kVecTileS + p;
+            if (s >= hw) continue;
+            float f[VD];
+#pragma unroll
+            for (int j = 0; j < VD; ++j) f[j] = tile[u * sub + (cv * VD + j) * PITCH + p];
+            const int64_t d = ((int64_t)n * pb.S + pb.geom.start[l] + s) * drow + (int64_t)h * pb.Dh + cv * VD;
+            *reinterpret_cast<uint4*>(dst + d * DES) = floats_to_vec<DBF>(f);
+        }
     }
 }
 
-template <bool DBF>
+template <bool DBF, int U>
 __global__ void __launch_bounds__(256)
 unpack_grad_vec_kernel(const Problem pb, const float* __restrict__ gv, const LevelViews dst, const TileMap64 tm) {
-    extern __shared__ float tile[];                   // [Dh][65]
+    extern __shared__ float tile[];                   // [U][Dh][65]
     constexpr int VD = ElemVec<DBF>::n, PITCH = kVecTileS + 1, DES = DBF ? 2 : 4;
     const int nh = blockIdx.y, n = nh / pb.H, h = nh % pb.H;
     int l = 0;
     while (l + 1 < pb.L && (int)blockIdx.x >= tm.first_tile[l + 1]) ++l;
-    const int s0 = ((int)blockIdx.x - tm.first_tile[l]) * kVecTileS;
+    const int s00 = ((int)blockIdx.x - tm.first_tile[l]) * (kVecTileS * U);
     const int hw = pb.geom.h[l] * pb.geom.w[l];
     const int64_t srow = (int64_t)pb.H * pb.Dh;
+    const int sub = pb.Dh * PITCH;
     for (int idx = threadIdx.x; idx < kVecTileS * (pb.Dh / 4); idx += 256) {
         const int p = idx / (pb.Dh / 4), cv = idx % (pb.Dh / 4);
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s0 + p < hw)
-            f = __ldg(reinterpret_cast<const float4*>(
-                gv + ((int64_t)n * pb.S + pb.geom.start[l] + s0 + p) * srow + (int64_t)h * pb.Dh + cv * 4));
-        tile[(cv * 4 + 0) * PITCH + p] = f.x; tile[(cv * 4 + 1) * PITCH + p] = f.y;
-        tile[(cv * 4 + 2) * PITCH + p] = f.z; tile[(cv * 4 + 3) * PITCH + p] = f.w;
+        float4 f[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = s00 + u * kVecTileS + p;
+            f[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < hw)
+                f[u] = __ldg(reinterpret_cast<const float4*>(
+                    gv + ((int64_t)n * pb.S + pb.geom.start[l] + s) * srow + (int64_t)h * pb.Dh + cv * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float* t = tile + u * sub + p;
+            t[(cv * 4 + 0) * PITCH] = f[u].x; t[(cv * 4 + 1) * PITCH] = f[u].y;
+            t[(cv * 4 + 2) * PITCH] = f[u].z; t[(cv * 4 + 3) * PITCH] = f[u].w;
+        }
     }
     __syncthreads();
     char* dp = reinterpret_cast<char*>(const_cast<void*>(dst.ptr[l]));
     for (int idx = threadIdx.x; idx < pb.Dh * (kVecTileS / VD); idx += 256) {
         const int c = idx / (kVecTileS / VD), v = idx % (kVecTileS / VD);
-        const int s = s0 + v * VD;
-        if (s >= hw) continue;
-        float f[VD];
+        const int64_t e0 = (int64_t)nh * dst.s_nh[l] + (int64_t)c * dst.s_c[l];
 #pragma unroll
-        for (int j = 0; j < VD; ++j) f[j] = tile[c * PITCH + v * VD + j];
-        const int64_t e = (int64_t)nh * dst.s_nh[l] + (int64_t)c * dst.s_c[l] + s;
-        if (s + VD <= hw) {
-            *reinterpret_cast<uint4*>(dp + e * DES) = floats_to_vec<DBF>(f);
-        } else {
+        for (int u = 0; u < U; ++u) {
+            const int s = s00 + u * kVecTileS + v * VD;
+            if (s >= hw) continue;
+            float f[VD];
 #pragma unroll
-            for (int j = 0; j < VD; ++j) if (s + j < hw) store_elem<DBF>(dp, e + j, f[j]);
+            for (int j = 0; j < VD; ++j) f[j] = tile[u * sub + c * PITCH + v * VD + j];
+            if (s + VD <= hw) {
+                *reinterpret_cast<uint4*>(dp + (e0 + s) * DES) = floats_to_vec<DBF>(f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VD; ++j) if (s + j < hw) store_elem<DBF>(dp, e0 + s + j, f[j]);
+            }
         }
     }
 }
@@ -270,12 +300,15 @@ static bool views_vectorisable(const Problem& pb, const LevelViews& v, bool bf16
     return true;
 }
 
-static TileMap64 make_tile_map64(const Problem& pb) {
+// sub-tiles per block: as many as keep the staging tile at or below 33 KB (Dh 32: 4, Dh 64: 2, Dh 128: 1)
+static int vec_sub_tiles(const Problem& pb) { return pb.Dh <= 32 ? 4 : pb.Dh <= 64 ? 2 : 1; }
+
+static TileMap64 make_tile_map64(const Problem& pb, int u) {
     TileMap64 tm;
     int acc = 0;
     for (int l = 0; l < pb.L; ++l) {
         tm.first_tile[l] = acc;
-        acc += (pb.geom.h[l] * pb.geom.w[l] + kVecTileS - 1) / kVecTileS;
+        acc += (pb.geom.h[l] * pb.geom.w[l] + kVecTileS * u - 1) / (kVecTileS * u);
     }
     for (int l = pb.L; l <= MSDA_MAX_LEVELS; ++l) tm.first_tile[l] = acc;
     return tm;
@@ -295,16 +328,20 @@ static TileMap make_tile_map(const Problem& pb) {
 cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void* dst, bool dst_bf16,
                    cudaStream_t st) {
     if (views_vectorisable(pb, src, src_bf16) && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-        const TileMap64 tm64 = make_tile_map64(pb);
+        const int u = vec_sub_tiles(pb);
+        const TileMap64 tm64 = make_tile_map64(pb, u);
         const dim3 grid(tm64.first_tile[pb.L], pb.N * pb.H);
-        const size_t smem = (size_t)pb.Dh * (kVecTileS + 1) * sizeof(float);
-        if (src_bf16) {
-            if (dst_bf16) repack_vec_kernel<true, true><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
-            else repack_vec_kernel<true, false><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
-        } else {
-            if (dst_bf16) repack_vec_kernel<false, true><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
-            else repack_vec_kernel<false, false><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);
+        const size_t smem = (size_t)u * pb.Dh * (kVecTileS + 1) * sizeof(float);
+#define MSDA_REPACK(U)                                                                                      \
+        if (src_bf16) {                                                                                     \
+            if (dst_bf16) repack_vec_kernel<true, true, U><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);   \
+            else repack_vec_kernel<true, false, U><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);     \
+        } else {                                                                                            \
+            if (dst_bf16) repack_vec_kernel<false, true, U><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);  \
+            else repack_vec_kernel<false, false, U><<<grid, 256, smem, st>>>(pb, src, tm64, (char*)dst);    \
         }
+        if (u == 4) { MSDA_REPACK(4) } else if (u == 2) { MSDA_REPACK(2) } else { MSDA_REPACK(1) }
+#undef MSDA_REPACK
         return cudaGetLastError();
     }
     const TileMap tm = make_tile_map(pb);
@@ -323,11 +360,15 @@ cudaError_t repack(const Problem& pb, const LevelViews& src, bool src_bf16, void
 cudaError_t unpack_grad(const Problem& pb, const float* grad_value, const LevelViews& dst, bool dst_bf16,
                         cudaStream_t st) {
     if (views_vectorisable(pb, dst, dst_bf16) && (reinterpret_cast<uintptr_t>(grad_value) & 15u) == 0) {
-        const TileMap64 tm64 = make_tile_map64(pb);
+        const int u = vec_sub_tiles(pb);
+        const TileMap64 tm64 = make_tile_map64(pb, u);
         const dim3 grid(tm64.first_tile[pb.L], pb.N * pb.H);
-        const size_t smem = (size_t)pb.Dh * (kVecTileS + 1) * sizeof(float);
-        if (dst_bf16) unpack_grad_vec_kernel<true><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);
-        else unpack_grad_vec_kernel<false><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);
+        const size_t smem = (size_t)u * pb.Dh * (kVecTileS + 1) * sizeof(float);
+#define MSDA_UNPACK(U)                                                                                      \
+        if (dst_bf16) unpack_grad_vec_kernel<true, U><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);  \
+        else unpack_grad_vec_kernel<false, U><<<grid, 256, smem, st>>>(pb, grad_value, dst, tm64);
+        if (u == 4) { MSDA_UNPACK(4) } else if (u == 2) { MSDA_UNPACK(2) } else { MSDA_UNPACK(1) }
+#undef MSDA_UNPACK
         return cudaGetLastError();
     }
     const TileMap tm = make_tile_map(pb);
