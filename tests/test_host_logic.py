@@ -184,3 +184,20 @@ def test_kernel_contract_routing_predicate():
     assert not patch._inside_kernel_contract(ok, torch.zeros(1, 3, 8, 2, 20, 2))      # 20 points
     assert not patch._inside_kernel_contract(ok, torch.zeros(1, 3, 8, 9, 4, 2))       # 9 levels
     assert not patch._inside_kernel_contract([v.double() for v in ok], loc)
+
+
+def test_division_magic_is_exact_in_the_range_the_kernels_use():
+    """csrc/msda_common.cuh `div_magic` / `fastdiv`: n // d == (n * ceil(2**32 / d)) >> 32 for every divisor the
+    C ABI accepts (L*P <= 8*16, H up to 64, P <= 16) and every numerator the forward forms (< 2**16: thread and
+    sample indices of a CTA, head index plus items per CTA)."""
+    import numpy as np
+    n = np.arange(0, 1 << 16, dtype=np.uint64)
+    for d in list(range(2, 130)) + [192, 255, 256, 1000, 4096]:
+        magic = np.uint64(((1 << 32) + d - 1) // d)
+        assert magic < (1 << 32)
+        assert np.array_equal((n * magic) >> np.uint64(32), n // np.uint64(d)), d
+    # worst case of the bound n * d < 2**32
+    for d in (3, 7, 12, 127):
+        top = np.arange((1 << 32) // d - 1000, (1 << 32) // d, dtype=np.uint64)
+        magic = np.uint64(((1 << 32) + d - 1) // d)
+        assert np.array_equal((top * magic) >> np.uint64(32), top // np.uint64(d)), d
