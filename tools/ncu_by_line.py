@@ -7,6 +7,7 @@ the library is compiled with -lineinfo) and sums per line of the kernel's own fi
 under the helper's file and line).
 
     python tools/ncu_by_line.py gpurun_out/r02_full.ncu-rep bwd_gather [top] > profiles/r02_bwd_by_source_line.txt
+    python tools/ncu_by_line.py gpurun_out/r02_full.ncu-rep bwd_gather 12 --shared   # bank-conflict wavefronts per line
 """
 import collections
 import csv
@@ -18,6 +19,7 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "detrpose_b200", "libmsda_b200.so")
+HEADER = []
 
 
 def sass_counts(rep, pattern):
@@ -27,6 +29,8 @@ def sass_counts(rep, pattern):
     for n, i in enumerate(heads):
         if re.search(pattern, rows[i][1]):
             end = heads[n + 1] if n + 1 < len(heads) else len(rows)
+            global HEADER
+            HEADER = rows[i + 1]
             return rows[i][1], rows[i + 2:end]
     raise SystemExit(f"no kernel matching {pattern!r} in {rep}")
 
@@ -62,9 +66,30 @@ def line_table(symbol):
     raise SystemExit(f"{symbol} not found in any cubin of {LIB}")
 
 
+def shared_conflicts(name, table, sass, header, top):
+    """Shared-memory wavefronts beyond the ideal count (bank-conflict replays), per source line and opcode."""
+    iw, ie = header.index("L1 Wavefronts Shared"), header.index("L1 Wavefronts Shared Excessive")
+    wav, exc, ops = collections.Counter(), collections.Counter(), collections.defaultdict(set)
+    for loc, r in zip(table, sass):
+        w = int(r[iw] or 0)
+        if w:
+            wav[loc] += w
+            exc[loc] += int(r[ie] or 0)
+            t = r[1].split()
+            ops[loc].add(t[1] if t[0].startswith("@") else t[0])
+    tw, te = sum(wav.values()), max(sum(exc.values()), 1)
+    print(f"# {name.split('(msda::Problem')[0]}\n# {tw / 1e6:.1f} M shared-memory wavefronts, {te / 1e6:.1f} M of them "
+          f"beyond the ideal count ({100 * te / tw:.1f} %); per source line: M excess, M total, % of all excess")
+    for loc, e in exc.most_common(top):
+        path = os.path.join(ROOT, "detrpose_b200", "csrc", loc[0]) if loc else ""
+        text = open(path).read().split("\n")[loc[1] - 1].strip()[:90] if path and os.path.exists(path) else ""
+        print(f"{e / 1e6:7.2f} {wav[loc] / 1e6:7.2f} {100 * e / te:5.1f}%  {loc[0]}:{loc[1]:<5d} {','.join(sorted(ops[loc])):22s} {text}")
+
+
 def main():
     rep, pattern = sys.argv[1], sys.argv[2]
-    top = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+    args = [a for a in sys.argv[3:] if not a.startswith("--")]
+    top = int(args[0]) if args else 60
     name, sass = sass_counts(rep, pattern)
     cands = mangled_candidates(name)
     if not cands:
@@ -72,6 +97,8 @@ def main():
     table = line_table(cands[0])
     if len(table) != len(sass):
         raise SystemExit(f"{len(sass)} instructions in the report, {len(table)} in the library: rebuild / re-profile")
+    if "--shared" in sys.argv:
+        return shared_conflicts(name, table, sass, HEADER, top)
     inst, smp = collections.Counter(), collections.Counter()
     for loc, r in zip(table, sass):
         inst[loc] += int(r[5])
