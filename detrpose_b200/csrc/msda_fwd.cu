@@ -488,8 +488,10 @@ static cudaError_t launch_lean(const Problem& pb, const void* value, const float
             // few queries per image: the slices get large and most of their rows are touched once or never;
             // the prefetch then costs more than the misses it saves (Len_q 300, 4 levels: 88 -> 98 us)
             if (pf.per_cta > 64 * 1024) pf.bytes = 0;
-            // a batch of pyramids that fits L2 is either resident already or read once anyway
-            if (pf.bytes <= (int64_t)l2) pf.bytes = 0;
+            // a batch of pyramids well inside L2 is likely resident already (the hint then only costs: +2-6 % on
+            // back-to-back launches at batch 8); from half of L2 on it pays even when it fits (training batch,
+            // 69 MB, cold L2: 64 -> 60 us)
+            if (pf.bytes <= (int64_t)l2 / 2) pf.bytes = 0;
         }
     }
     auto launch = [&](auto kern) -> cudaError_t {
