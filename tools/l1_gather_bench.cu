@@ -20,10 +20,13 @@ __device__ __forceinline__ uint32_t smid() { uint32_t r; asm("mov.u32 %0, %%smid
 // MODE 2: 8 lanes x 16 B = rows r, r+1 (128 contiguous bytes at a 64-byte-aligned address)
 // MODE 3: 4 lanes x 32 B (LDG.256) = rows r, r+1
 // MODE 4: 2 lanes x 32 B (LDG.256) = one 64-byte row
-template <int MODE>
+// MODE 5: 4 lanes x 32 B (LDG.256) = row r and row r + 8 (channel-last: the next pixel of the same head, +512 B)
+// PM: channel-last addressing of the model -- the 8 heads of a pixel are 8 consecutive 64-byte rows, a group of
+// lanes works on ONE head (group index mod 8) and picks random pixels, as an item of the forward does
+template <int MODE, bool PM = false>
 __global__ void gather_kernel(const uint4* __restrict__ buf, uint32_t window_rows, uint32_t n_windows, bool per_sm,
                               int iters, float* __restrict__ sink) {
-    constexpr int G = MODE == 2 ? 8 : MODE == 4 ? 2 : 4;
+    constexpr int G = MODE == 2 ? 8 : MODE == 4 ? 2 : 4;      // lanes per group (MODE 5: 4 lanes, two rows)
     const int lane = threadIdx.x % G;
     const uint32_t grp = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const uint32_t w = per_sm ? smid() % n_windows : hash32(blockIdx.x * 2654435761u) % n_windows;
@@ -33,14 +36,16 @@ __global__ void gather_kernel(const uint4* __restrict__ buf, uint32_t window_row
 #pragma unroll 4
     for (int i = 0; i < iters; ++i) {
         s = s * 1664525u + 1013904223u;
-        const uint32_t row = hash32(s) % (window_rows - 1);
+        uint32_t row = hash32(s) % (window_rows - 16);
+        if (PM) row = (row & ~7u) | (grp & 7u);
         uint4 v;
         if (MODE == 1) v = base[row * 4 + lane];
         else if (MODE >= 3) {
             uint4 u;
+            const uint4* p = MODE == 5 ? base + (row + (lane >> 1) * 8) * 4 + (lane & 1) * 2 : base + row * 4 + lane * 2;
             asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w), "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                         : "l"(base + row * 4 + lane * 2));
+                         : "l"(p));
             v.x ^= u.x; v.w ^= u.w;
         }
         else v = __ldg(base + row * 4 + lane);
@@ -92,6 +97,22 @@ int main() {
             printf("{\"resident_threads_per_sm\":2048,\"smem_per_sm_KB\":%d,\"ldg128_64B_Grows_s\":%.1f,\"ldg256_pair128B_Grows_s\":%.1f,\"ldg256_64B_Grows_s\":%.1f}\n",
                    total_kb, (double)grid0 * threads0 / 4 * iters0 / a / 1e6, (double)grid0 * threads0 / 4 * iters0 * 2 / b / 1e6,
                    (double)grid0 * threads0 / 2 * iters0 / c / 1e6);
+        }
+        {
+            const float a = time_ms([&] { gather_kernel<0, true><<<grid0, threads0, 100 * 1024 / 8>>>(buf0, wrows, nwin, false, iters0, sink0); });
+            const float c = time_ms([&] { gather_kernel<4, true><<<grid0, threads0, 100 * 1024 / 8>>>(buf0, wrows, nwin, false, iters0, sink0); });
+            const float d = time_ms([&] { gather_kernel<5, true><<<grid0, threads0, 100 * 1024 / 8>>>(buf0, wrows, nwin, false, iters0, sink0); });
+            printf("{\"addressing\":\"channel-last, 4 lanes x 32 B = the rows of pixel x and x + 1 of one head (+512 B)\",\"ldg256_2rows_Grows_s\":%.1f}\n",
+                   (double)grid0 * threads0 / 4 * iters0 * 2 / d / 1e6);
+            const size_t smem4 = (size_t)(228 * 1024 / 5) + 1024;        // 4 resident CTAs = 1024 threads, as the forward
+            CK(cudaFuncSetAttribute(gather_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            CK(cudaFuncSetAttribute(gather_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+            const float a4 = time_ms([&] { gather_kernel<0, true><<<grid0, threads0, smem4>>>(buf0, wrows, nwin, false, iters0, sink0); });
+            const float c4 = time_ms([&] { gather_kernel<4, true><<<grid0, threads0, smem4>>>(buf0, wrows, nwin, false, iters0, sink0); });
+            printf("{\"addressing\":\"channel-last (pixel, head) rows, one head per lane group\",\"smem_per_sm_KB\":100,"
+                   "\"ldg128_64B_Grows_s\":%.1f,\"ldg256_64B_Grows_s\":%.1f,\"ldg128_64B_1024thr_186KB_Grows_s\":%.1f,\"ldg256_64B_1024thr_186KB_Grows_s\":%.1f}\n",
+                   (double)grid0 * threads0 / 4 * iters0 / a / 1e6, (double)grid0 * threads0 / 2 * iters0 / c / 1e6,
+                   (double)grid0 * threads0 / 4 * iters0 / a4 / 1e6, (double)grid0 * threads0 / 2 * iters0 / c4 / 1e6);
         }
         for (int ctas : {6, 4, 3, 2}) {
             // 228 KB / (ctas + 1) < smem per CTA <= 228 KB / ctas limits residency; use the smallest such size
